@@ -1,0 +1,306 @@
+"""``SwarmEnv`` - the reference's DirectMARLEnv-style task API on top of the fused CUDA step.
+
+Host-side mirror of the duck-typed protocol the reference trainers and scripts rely on
+(agents/poca_trainer.py:204-222,376,509,575,619 of the reference):
+
+* ``reset() -> (obs_dict, info)``, ``step(action_dict) -> (obs, reward, terminated, truncated, info)``
+  with per-agent dicts keyed ``epuck_0..epuck_19``; ``obs_dict[a]`` is an ``(E, obs_dim)`` view.
+* ``unwrapped`` -> self, ``cfg``, ``device``, ``num_envs``, ``scene.num_envs``, ``max_episode_length``,
+  ``episode_length_buf``, ``get_critic_state()``, ``completed_terminal_critic_state``,
+  ``completed_group_reward``, ``agent_pos``, ``agent_yaw``, ``prev_ground_color``.
+* the seven Gymnasium ids of missions/*/__init__.py via :func:`make` (and ``gym.register`` when
+  gymnasium is importable), each with the ``env_cfg_entry_point`` kwarg.
+
+All state lives in torch-owned device tensors; the extension borrows raw pointers for the duration
+of a call and enqueues on torch's current stream without synchronising.  There is no CPU fallback:
+constructing the env without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import types
+
+import torch
+
+from . import _lib
+from .cfg import TASK_CFGS, DirectionalGateEnvCfg
+from .params import N, SwarmNoise, SwarmOut, SwarmState, build_params, pack_fsm, unpack_fsm
+
+_AGENTS = [f"epuck_{i}" for i in range(N)]
+
+
+class SwarmEnv:
+    """Batched 20-e-puck swarm environment (five missions, five CASA variants)."""
+
+    metadata = {"render_modes": [None]}
+
+    def __init__(self, cfg: DirectionalGateEnvCfg | None = None, render_mode: str | None = None,
+                 env_offset: int = 0, **kwargs):
+        if cfg is None:
+            cfg = DirectionalGateEnvCfg()
+        self.cfg = cfg
+        self.render_mode = render_mode
+        self.device = torch.device(cfg.sim.device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError(
+                "SwarmEnv runs only on a CUDA device (the fused sm_100a step has no CPU fallback); "
+                f"cfg.sim.device={cfg.sim.device!r}, torch.cuda.is_available()={torch.cuda.is_available()}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _lib.load()
+        self.params = build_params(cfg)
+        self.num_envs = int(cfg.scene.num_envs)
+        self.scene = types.SimpleNamespace(num_envs=self.num_envs)
+        self.sim = types.SimpleNamespace(has_gui=lambda: False, device=str(self.device))
+        self.max_episode_length = math.ceil(cfg.episode_length_s / (cfg.sim.dt * cfg.decimation))
+        self.possible_agents = list(cfg.possible_agents)
+        self.agents = list(cfg.possible_agents)
+        self.num_agents = N
+        self.extras: dict = {}
+
+        E, dev = self.num_envs, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.agent_pos = torch.zeros(E, N, 2, **f32)
+        self.agent_yaw = torch.zeros(E, N, **f32)
+        self.prev_ground_color = torch.full((E, N), 0.5, **f32)
+        self._cached_left_vel = torch.zeros(E, N, **f32)
+        self._cached_right_vel = torch.zeros(E, N, **f32)
+        self._fsm = torch.zeros(E, N, dtype=torch.int32, device=dev)
+        self._beh_cache = torch.zeros(E, 6, N, **f32)
+        self._mission_flags = torch.zeros(E, N, dtype=torch.uint8, device=dev)
+        self.episode_length_buf = torch.zeros(E, dtype=torch.long, device=dev)
+        self._episode_group_reward = torch.zeros(E, **f32)
+        self.completed_group_reward = torch.zeros(E, **f32)
+        self.completed_terminal_critic_state = torch.zeros(E, N, 5, **f32)
+        self._scratch = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.reset_buf = torch.zeros(E, dtype=torch.bool, device=dev)
+
+        self.obs_dim = int(self.params.obs_dim)
+        self.act_dim = 1 if self.params.discrete_actions else 2
+        self._obs = torch.zeros(E, N, self.obs_dim, **f32)
+        self._reward = torch.zeros(E, **f32)
+        self._time_out = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self._critic = torch.zeros(E, N, 5, **f32)
+        self._terminated = torch.zeros(E, dtype=torch.bool, device=dev)
+        self._act_buf = torch.zeros(E, N, self.act_dim, dtype=torch.long if self.params.discrete_actions else torch.float32,
+                                    device=dev)
+
+        self._state = SwarmState(
+            self.agent_pos.data_ptr(), self.agent_yaw.data_ptr(), self.prev_ground_color.data_ptr(),
+            self._cached_left_vel.data_ptr(), self._cached_right_vel.data_ptr(), self._fsm.data_ptr(),
+            self._beh_cache.data_ptr(), self._mission_flags.data_ptr(), self.episode_length_buf.data_ptr(),
+            self._episode_group_reward.data_ptr(), self.completed_group_reward.data_ptr(),
+            self.completed_terminal_critic_state.data_ptr(), self._scratch.data_ptr())
+        self._out = SwarmOut(self._obs.data_ptr(), self._reward.data_ptr(), self._time_out.data_ptr())
+        self._seed = int(cfg.seed) if getattr(cfg, "seed", None) is not None else 0
+        self._step_counter = 0
+        self._env_offset = int(env_offset)
+        self._injected: dict = {}
+        self._obs_views = {a: self._obs[:, i] for i, a in enumerate(self.possible_agents)}
+
+    # ── protocol ────────────────────────────────────────────────────────────────────────────
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def _has_food(self):  # FOR:36
+        return (self._mission_flags & 1).bool()
+
+    @property
+    def _prev_in_nest(self):  # FOR:37
+        return ((self._mission_flags >> 1) & 1).bool()
+
+    @property
+    def behavior_state(self) -> dict:
+        """Unpacked behaviour-module state machines (BEH:141-153 field names)."""
+        return unpack_fsm(self._fsm)
+
+    def set_behavior_state(self, **fields):
+        cur = self.behavior_state
+        cur.update({k: torch.as_tensor(v, device=self.device) for k, v in fields.items()})
+        self._fsm.copy_(pack_fsm(cur["_explore_state"], cur["_explore_steps"], cur["_explore_dir"],
+                                 cur["_photo_avoiding"], cur["_photo_steps"], cur["_photo_dir"],
+                                 cur["_antiphoto_avoiding"], cur["_antiphoto_steps"], cur["_antiphoto_dir"]))
+
+    def seed(self, seed: int):
+        self._seed = int(seed)
+
+    def inject_noise(self, rab_u=None, turn_dur=None, spawn_u=None, yaw_u=None):
+        """Parity mode: use these draws for the NEXT step/reset instead of the Philox stream."""
+        E, dev = self.num_envs, self.device
+        inj = {}
+        if rab_u is not None:
+            inj["rab_u"] = torch.as_tensor(rab_u, dtype=torch.float32, device=dev).reshape(E, N, N).contiguous()
+        if turn_dur is not None:
+            inj["turn_dur"] = torch.as_tensor(turn_dur, device=dev).to(torch.int32).reshape(E, N, 3).contiguous()
+        if spawn_u is not None:
+            inj["spawn_u"] = torch.as_tensor(spawn_u, dtype=torch.float32, device=dev).reshape(-1, E, N, 2).contiguous()
+        if yaw_u is not None:
+            inj["yaw_u"] = torch.as_tensor(yaw_u, dtype=torch.float32, device=dev).reshape(E, N).contiguous()
+        self._injected = inj
+
+    def _noise(self) -> SwarmNoise:
+        inj, self._injected = self._injected, {}
+        self._noise_keepalive = inj
+        nz = SwarmNoise()
+        for k in ("rab_u", "turn_dur", "spawn_u", "yaw_u"):
+            if k in inj:
+                setattr(nz, k, inj[k].data_ptr())
+        nz.spawn_rounds = inj["spawn_u"].shape[0] if "spawn_u" in inj else 0
+        nz.seed = self._seed
+        nz.step_counter = self._step_counter
+        nz.env_offset = self._env_offset
+        self._step_counter += 1
+        return nz
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, seed: int | None = None, options: dict | None = None):
+        if seed is not None:
+            self._seed = int(seed)
+        nz = self._noise()
+        with torch.cuda.device(self.device):
+            rc = self._lib.swarm_reset(C.byref(self.params), C.byref(self._state), C.byref(nz), C.byref(self._out),
+                                       self.num_envs, self._stream())
+        _lib.check(rc, "swarm_reset")
+        return dict(self._obs_views), self.extras
+
+    def _gather_actions(self, actions) -> torch.Tensor:
+        """Return an (E,N,act) contiguous tensor of the right dtype, zero-copy when ``actions`` is
+        the usual dict of 20 strided views of one tensor (agents/poca_trainer.py:559)."""
+        want = torch.long if self.params.discrete_actions else torch.float32
+        E, A = self.num_envs, self.act_dim
+        if isinstance(actions, torch.Tensor):
+            t = actions.reshape(E, N, A)
+            if t.dtype != want or not t.is_contiguous() or t.device != self.device:
+                self._act_buf.copy_(t)
+                t = self._act_buf
+            return t
+        a0 = actions[self.possible_agents[0]]
+        if (a0.dtype == want and a0.device == self.device and tuple(a0.shape) == (E, A)
+                and a0.stride() == (N * A, 1)):
+            base, isz = a0.data_ptr(), a0.element_size()
+            if all(actions[a].data_ptr() == base + i * A * isz and actions[a].stride() == (N * A, 1)
+                   and actions[a].dtype == want for i, a in enumerate(self.possible_agents)):
+                # read during the call; callers may mutate their views afterwards (scripts/play.py:702)
+                return torch.as_strided(a0, (E, N, A), (N * A, A, 1))
+        for i, a in enumerate(self.possible_agents):
+            self._act_buf[:, i] = actions[a].reshape(E, A)
+        return self._act_buf
+
+    def step_tensor(self, actions: torch.Tensor):
+        """One env.step from an (E,N,act) action tensor; returns (obs (E,N,obs), reward (E), time_out (E) bool)
+        views of buffers that the next step overwrites."""
+        act = self._gather_actions(actions)
+        nz = self._noise()
+        with torch.cuda.device(self.device):
+            rc = self._lib.swarm_step(C.byref(self.params), C.byref(self._state), C.c_void_p(act.data_ptr()),
+                                      C.byref(nz), C.byref(self._out), self.num_envs, self._stream())
+        _lib.check(rc, "swarm_step")
+        return self._obs, self._reward, self._time_out.view(torch.bool)
+
+    def step(self, actions: dict):
+        _, reward, time_out = self.step_tensor(actions)
+        agents = self.possible_agents
+        reward_dict = dict.fromkeys(agents, reward)
+        terminated = dict.fromkeys(agents, self._terminated)
+        truncated = dict.fromkeys(agents, time_out)
+        return dict(self._obs_views), reward_dict, terminated, truncated, self.extras
+
+    def rollout(self, actions: torch.Tensor, steps: int | None = None):
+        """``steps`` consecutive env.steps with device-resident actions (T,E,N,act) (or one (E,N,act)
+        action repeated, the trainers' decision_period loop).  Returns (last obs, summed reward, OR-ed time_out)."""
+        want = torch.long if self.params.discrete_actions else torch.float32
+        E, A = self.num_envs, self.act_dim
+        if actions.dtype != want or actions.device != self.device:
+            actions = actions.to(device=self.device, dtype=want)
+        actions = actions.contiguous()
+        if actions.dim() == 4 or (actions.dim() == 3 and actions.shape[0] != E):
+            T = actions.shape[0]
+            stride = E * N * A
+        else:
+            T, stride = int(steps), 0
+        if steps is not None:
+            T = int(steps)
+        nz = self._noise()
+        self._step_counter += T - 1
+        with torch.cuda.device(self.device):
+            rc = self._lib.swarm_rollout(C.byref(self.params), C.byref(self._state), C.c_void_p(actions.data_ptr()),
+                                         stride, C.byref(nz), C.byref(self._out), E, T, self._stream())
+        _lib.check(rc, "swarm_rollout")
+        return self._obs, self._reward, self._time_out.view(torch.bool)
+
+    def get_critic_state(self) -> torch.Tensor:
+        """(E,N,5) = (rho, cos alpha, sin alpha, cos beta, sin beta), ENV:1279-1290."""
+        out = torch.empty(self.num_envs, N, 5, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.swarm_critic_state(C.byref(self.params), C.byref(self._state), C.c_void_p(out.data_ptr()),
+                                              self.num_envs, self._stream())
+        _lib.check(rc, "swarm_critic_state")
+        return out
+
+    def close(self):
+        pass
+
+    # ── teacher-forcing helpers for the parity tests ────────────────────────────────────────
+    def load_state(self, state: dict):
+        """Overwrite the device state from host arrays in the include/swarm_abi.h layouts."""
+        m = {
+            "pos": self.agent_pos, "yaw": self.agent_yaw, "prev_ground": self.prev_ground_color,
+            "cached_left": self._cached_left_vel, "cached_right": self._cached_right_vel, "fsm": self._fsm,
+            "beh_cache": self._beh_cache, "mission_flags": self._mission_flags,
+            "episode_length_buf": self.episode_length_buf, "episode_group_reward": self._episode_group_reward,
+            "completed_group_reward": self.completed_group_reward,
+            "completed_terminal_critic_state": self.completed_terminal_critic_state,
+        }
+        for k, dst in m.items():
+            dst.copy_(torch.as_tensor(state[k]).to(dst.dtype).reshape(dst.shape))
+
+    def dump_state(self) -> dict:
+        m = {
+            "pos": self.agent_pos, "yaw": self.agent_yaw, "prev_ground": self.prev_ground_color,
+            "cached_left": self._cached_left_vel, "cached_right": self._cached_right_vel, "fsm": self._fsm,
+            "beh_cache": self._beh_cache, "mission_flags": self._mission_flags,
+            "episode_length_buf": self.episode_length_buf, "episode_group_reward": self._episode_group_reward,
+            "completed_group_reward": self.completed_group_reward,
+            "completed_terminal_critic_state": self.completed_terminal_critic_state,
+        }
+        return {k: v.detach().cpu().numpy().copy() for k, v in m.items()}
+
+
+# ── registry (missions/*/__init__.py of the reference) ─────────────────────────────────────────
+registry = {
+    task_id: {
+        "entry_point": f"{__name__}:SwarmEnv",
+        "disable_env_checker": True,
+        "kwargs": {"env_cfg_entry_point": f"{cfg_cls.__module__}:{cfg_cls.__name__}"},
+    }
+    for task_id, cfg_cls in TASK_CFGS.items()
+}
+
+
+def make(task_id: str, cfg=None, **kwargs) -> SwarmEnv:
+    """``gym.make(task_id, cfg=cfg)`` equivalent that needs no gymnasium install."""
+    if task_id not in TASK_CFGS:
+        raise KeyError(f"unknown task {task_id!r}; known: {sorted(TASK_CFGS)}")
+    if cfg is None:
+        cfg = TASK_CFGS[task_id]()
+    elif not isinstance(cfg, TASK_CFGS[task_id]):
+        raise TypeError(f"{task_id} expects a {TASK_CFGS[task_id].__name__}, got {type(cfg).__name__}")
+    return SwarmEnv(cfg, **kwargs)
+
+
+def register_gym() -> bool:
+    """Register the seven ids with gymnasium when it is installed; returns False otherwise."""
+    try:
+        import gymnasium as gym
+    except ImportError:
+        return False
+    for task_id, spec in registry.items():
+        if task_id not in gym.registry:
+            gym.register(id=task_id, entry_point=spec["entry_point"], disable_env_checker=True,
+                         kwargs=dict(spec["kwargs"]))
+    return True

@@ -1,0 +1,121 @@
+"""GPU parity at scale: CUDA step vs the CPU oracle on seeded random rollouts (teacher-forced per step),
+plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+import fixtures
+from oracle import oracle
+from swarmacb_isaaclab_b200.params import N
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("hom", "lily", 1), ("for", "daisy", 1), ("dgt", "dandelion", 1), ("shl", "oc2", 1),
+    ("xor", "cyclamen", 1), ("shl", "daisy", 2), ("dgt", "daisy", 1), ("xor", "oc2c", 1),
+]
+
+
+def _mk(mission, mode, E, dec=1):
+    from swarmacb_isaaclab_b200.env import SwarmEnv
+    return SwarmEnv(fixtures.make_cfg(mission, mode, E, dec, device="cuda:0"))
+
+
+def _cluster(rng, E, frac=0.5):
+    """Half of the envs get a tight robot cluster so that collisions / rays / RAB are busy."""
+    spawn = rng.random((6, E, N, 2), dtype=np.float32)
+    k = int(E * frac)
+    c = rng.random((k, 1, 2), dtype=np.float32) * 0.8 + 0.1
+    spawn[:, :k] = c + (spawn[:, :k] - 0.5) * 0.12
+    return spawn
+
+
+@pytest.mark.parametrize("mission,mode,dec", CASES)
+def test_cuda_vs_oracle_rollout(mission, mode, dec):
+    E, T = 384, 12
+    rng = np.random.default_rng(hash((mission, mode)) % 2**31)
+    env = _mk(mission, mode, E, dec)
+    p = env.params
+    host = oracle.new_state(E)
+    spawn_u, yaw_u = _cluster(rng, E), rng.random((E, N), dtype=np.float32)
+    rab_u = rng.random((E, N, N), dtype=np.float32)
+    env.inject_noise(rab_u=rab_u, spawn_u=spawn_u, yaw_u=yaw_u)
+    env.reset()
+    obs_o = oracle.reset(p, host, rab_u=rab_u, spawn_u=spawn_u, yaw_u=yaw_u)
+    torch.cuda.synchronize()
+    dev = env.dump_state()
+    assert np.abs(dev["pos"] - host["pos"]).max() <= fixtures.POS_TOL
+    assert np.abs(env._obs.cpu().numpy() - obs_o).max() <= fixtures.SENSOR_TOL
+    # push some envs close to the time limit so that partial resets happen inside the window
+    host["episode_length_buf"][::7] = p.max_episode_length - 5
+    host["episode_length_buf"][3::11] = p.max_episode_length - 9
+    for t in range(T):
+        env.load_state(host)  # teacher-forced: both sides start every step from the oracle's state
+        if p.discrete_actions:
+            act = rng.integers(0, 6, (E, N), dtype=np.int64)
+        else:
+            act = (rng.random((E, N, 2), dtype=np.float32) * 2.4 - 1.2).astype(np.float32)
+        rab_u = rng.random((E, N, N), dtype=np.float32)
+        dur = rng.integers(1, 5, (E, N, 3)).astype(np.int32)
+        spawn_u, yaw_u = _cluster(rng, E), rng.random((E, N), dtype=np.float32)
+        env.inject_noise(rab_u=rab_u, turn_dur=dur, spawn_u=spawn_u, yaw_u=yaw_u)
+        obs, rew, to = env.step_tensor(torch.as_tensor(act, device="cuda:0"))
+        obs_o, rew_o, to_o = oracle.step(p, host, act, rab_u=rab_u, turn_dur=dur, spawn_u=spawn_u, yaw_u=yaw_u)
+        crit = env.get_critic_state().cpu().numpy()
+        torch.cuda.synchronize()
+        dev = env.dump_state()
+        lab = f"{mission}/{mode} t={t}"
+        assert np.abs(dev["pos"] - host["pos"]).max() <= fixtures.POS_TOL, lab
+        assert fixtures.angle_diff(dev["yaw"], host["yaw"]).max() <= fixtures.YAW_TOL, lab
+        for k in ("fsm", "mission_flags", "episode_length_buf", "prev_ground", "episode_group_reward",
+                  "completed_group_reward"):
+            assert np.array_equal(dev[k], host[k]), f"{lab}: {k}"
+        assert np.array_equal(rew.cpu().numpy(), rew_o), lab
+        assert np.array_equal(to.cpu().numpy(), to_o), lab
+        assert np.abs(obs.cpu().numpy() - obs_o).max() <= fixtures.SENSOR_TOL, lab
+        assert np.abs(crit - oracle.critic_state(p, host)).max() <= 2e-5, lab
+        assert np.abs(dev["completed_terminal_critic_state"] - host["completed_terminal_critic_state"]).max() <= 2e-5
+
+
+@pytest.mark.parametrize("mission,mode,E", [("hom", "lily", 4096), ("for", "daisy", 16384), ("dgt", "dandelion", 8192)])
+def test_full_size_properties(mission, mode, E):
+    """BASELINE-size rollouts with in-kernel Philox noise: invariants that need no oracle."""
+    env = _mk(mission, mode, E)
+    p = env.params
+    env.reset(seed=3)
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    total = torch.zeros(E, device="cuda:0")
+    for t in range(30):
+        if p.discrete_actions:
+            act = torch.randint(0, 6, (E, N, 1), generator=g, device="cuda:0")
+        else:
+            act = torch.rand(E, N, 2, generator=g, device="cuda:0") * 2 - 1
+        obs, rew, to = env.step_tensor(act)
+        total += rew
+    torch.cuda.synchronize()
+    pos = env.agent_pos
+    assert torch.isfinite(pos).all() and torch.isfinite(obs).all()
+    inr = 1.2357309
+    assert (pos.norm(dim=-1) <= inr / np.cos(np.pi / 12) + 1e-3).all()          # inside the circumcircle
+    d = (pos.unsqueeze(2) - pos.unsqueeze(1)).norm(dim=-1) + torch.eye(N, device=pos.device) * 10
+    assert (d.min() > 0.03)                                                       # solver keeps robots apart
+    assert (env.agent_yaw.abs() <= np.pi + 1e-6).all()
+    assert (env.episode_length_buf == 30).all()
+    assert torch.equal(rew, rew.round()) and (rew >= -N).all() and (rew <= N).all()  # integer-valued counters
+    assert torch.allclose(env._episode_group_reward, total)
+    zt = obs[..., 19] if p.obs_dim == 24 else obs[..., 3]
+    assert (zt >= 0).all() and (zt < 1).all()
+    # packet loss p=0.85: mean neighbour count must be far below the no-loss count
+    keep_rate = float((zt > 0).float().mean())
+    assert 0.02 < keep_rate < 0.9
+    # determinism: same seed, same actions -> identical trajectory; different shard offset -> different noise
+    env2 = _mk(mission, mode, E)
+    env2.reset(seed=3)
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    for t in range(30):
+        if p.discrete_actions:
+            act = torch.randint(0, 6, (E, N, 1), generator=g, device="cuda:0")
+        else:
+            act = torch.rand(E, N, 2, generator=g, device="cuda:0") * 2 - 1
+        obs2, _, _ = env2.step_tensor(act)
+    assert torch.equal(env2.agent_pos, env.agent_pos) and torch.equal(obs2, obs)

@@ -1,0 +1,132 @@
+"""CPU-only checks: cfg mirror, params derivation, fsm packing, C-ABI exports, no-fallback behaviour."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import swarmacb_isaaclab_b200 as pkg
+from swarmacb_isaaclab_b200 import build as cuda_build
+from swarmacb_isaaclab_b200 import params as P
+from swarmacb_isaaclab_b200.cfg import TASK_CFGS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_task_ids_and_cfg_entry_points():
+    assert set(TASK_CFGS) == {
+        "SwarmACB-DirectionalGate-v0", "SwarmACB-XOR-v0", "SwarmACB-Homing-v0", "SwarmACB-Foraging-v0",
+        "SwarmACB-Sheltering-v0", "SwarmACB-SCA-v0", "SwarmACB-SHL-v0"}
+    from swarmacb_isaaclab_b200 import env
+    for tid, spec in env.registry.items():
+        mod, cls = spec["kwargs"]["env_cfg_entry_point"].split(":")
+        assert getattr(__import__(mod, fromlist=[cls]), cls) is TASK_CFGS[tid]
+
+
+def test_variants_and_spaces():
+    cfg = pkg.DirectionalGateEnvCfg()
+    assert cfg.num_agents == 20 and cfg.possible_agents[0] == "epuck_0" and not cfg.discrete_actions
+    for v, (od, ad) in {"dandelion": (24, 2), "daisy": (24, 1), "lily": (4, 1), "tulip": (4, 1), "cyclamen": (4, 1)}.items():
+        cfg.update_variant(v)
+        assert cfg.observation_spaces["epuck_19"] == od and cfg.action_spaces["epuck_0"] == ad
+        assert cfg.discrete_actions == (v != "dandelion")
+        assert P.build_params(cfg).obs_dim == od
+    cfg.update_variant("cyclamen")
+    cfg.use_continuous_actions(full_observations=True)
+    p = P.build_params(cfg)
+    assert (p.obs_dim, p.discrete_actions) == (24, 0) and cfg.action_spaces["epuck_3"] == 2
+    cfg.use_continuous_actions(full_observations=False)
+    assert P.build_params(cfg).obs_dim == 4
+
+
+def test_episode_lengths_and_constants():
+    want = {"dgt": 1200, "xor": 1800, "hom": 1200, "for": 1800, "shl": 1800}
+    for m, cls in pkg.MISSION_CFGS.items():
+        cfg = cls()
+        p = P.build_params(cfg)
+        assert p.max_episode_length == want[m]
+        assert p.n_segments == 12 + p.n_internal
+        assert abs(p.wall_r_eff - 0.0401) < 1e-7 and abs(p.two_radius - 0.07) < 1e-8
+        assert math.isclose(cfg.arena_circumradius, math.sqrt(4.91 / 3), rel_tol=1e-12)
+    assert P.build_params(pkg.ShelteringEnvCfg()).capsule_clearance == pytest.approx(0.0501)
+    assert P.build_params(pkg.DirectionalGateEnvCfg()).capsule_clearance == pytest.approx(0.0401)
+    assert P.build_params(pkg.XorAggregationEnvCfg()).gate_mode == P.GATE_DGT  # inherited push-out quirk
+    cfg = pkg.DirectionalGateEnvCfg()
+    cfg.decimation = 6
+    assert P.build_params(cfg).max_episode_length == 200
+
+
+def test_sensor_tables_are_float32_torch_results():
+    cos_a, sin_a, rc, rs = P.sensor_tables()
+    assert cos_a.dtype == np.float32 and cos_a[2] != 0.0 and abs(cos_a[2]) < 1e-7  # cos(float32(pi/2))
+    assert sin_a[2] == -1.0 and rc[0] == pytest.approx(math.sqrt(0.5), abs=1e-7)
+
+
+def test_fsm_pack_roundtrip():
+    g = torch.Generator().manual_seed(0)
+    E, N = 5, 20
+    f = dict(
+        es=torch.randint(0, 2, (E, N), generator=g), est=torch.randint(0, 5, (E, N), generator=g),
+        ed=torch.randint(-1, 2, (E, N), generator=g).float(), pa=torch.randint(0, 2, (E, N), generator=g).bool(),
+        ps=torch.randint(0, 5, (E, N), generator=g), pd=torch.randint(-1, 2, (E, N), generator=g).float(),
+        aa=torch.randint(0, 2, (E, N), generator=g).bool(), as_=torch.randint(0, 5, (E, N), generator=g),
+        ad=torch.randint(-1, 2, (E, N), generator=g).float())
+    w = P.pack_fsm(*f.values())
+    u = P.unpack_fsm(w)
+    for got, want in zip(u.values(), f.values()):
+        assert torch.equal(got.float(), want.float())
+
+
+def test_abi_header_matches_ctypes_layout():
+    hdr = open(os.path.join(ROOT, "include", "swarm_abi.h")).read()
+    for struct, cls in (("SwarmParams", P.SwarmParams), ("SwarmState", P.SwarmState), ("SwarmNoise", P.SwarmNoise),
+                        ("SwarmOut", P.SwarmOut)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*?\]", "", part.strip().split()[-1].lstrip("*")))
+        assert names == [f[0] for f in cls._fields_], struct
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from swarmacb_isaaclab_b200 import _lib
+    path = cuda_build.build()
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "swarm_abi.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*) (swarm_\w+)\(", hdr, re.M))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    lib.swarm_abi_version.restype = ctypes.c_int
+    assert lib.swarm_abi_version() == P.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from swarmacb_isaaclab_b200.env import SwarmEnv, make
+    cfg = pkg.HomingEnvCfg()
+    cfg.sim.device = "cpu"
+    with pytest.raises(RuntimeError):
+        SwarmEnv(cfg)
+    with pytest.raises(RuntimeError):
+        make("SwarmACB-Homing-v0")
+    with pytest.raises(KeyError):
+        make("SwarmACB-Nope-v0")
+
+
+def test_product_never_imports_oracle():
+    src_dir = os.path.join(ROOT, "swarmacb-isaaclab_b200")
+    for dirpath, _, files in os.walk(src_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no CPU or eager-torch fallback", ""), f
