@@ -78,6 +78,8 @@ typedef struct SwarmParams {
   float prox_threshold;          /* BEH:116 */
   /* sensor geometry, float32 results of torch ops on float32 angles (SENS:75-79) */
   float cos_a[8], sin_a[8], rab_cos[4], rab_sin[4];
+  /* ztilde = 1 - 2/(1+exp(n)) for n = 0..19 neighbours, float32 torch results (SENS:425) */
+  float ztilde_lut[SWARM_N];
   /* arena faces (ENV:849-872) */
   float face_nx[12], face_ny[12], face_px[12], face_py[12];
   /* all raycast segments: ax, ay, bx, by and bx-ax, by-ay in float32 (SENS:204-213) */

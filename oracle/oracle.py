@@ -20,8 +20,9 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH) or (
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "swarm_oracle.c"))):
+    deps = (os.path.join(_HERE, "swarm_oracle.c"), os.path.join(_HERE, "..", "include", "swarm_abi.h"))
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(d) for d in deps):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
     return _LIB_PATH
 

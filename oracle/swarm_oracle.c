@@ -12,9 +12,9 @@
  * pinned by no reference-owned test.
  *
  * Plain C99, float32 scalar arithmetic in the reference's operation order; build with
- * -ffp-contract=off so no FMA is formed.  Transcendentals come from libm (sinf/cosf/atan2f/expf),
- * the reference's from SLEEF: last-ulp differences are expected and covered by the stated
- * tolerances (1e-5 m / 1e-5 rad poses, 1e-4 sensors); integer state is exact.
+ * -ffp-contract=off so no FMA is formed.  sin/cos/atan2 are correctly rounded (double libm, one
+ * rounding), the reference's come from SLEEF (<= 1 ulp): last-ulp differences are expected and
+ * covered by the stated tolerances (1e-5 m / 1e-5 rad poses, 1e-4 sensors); integer state is exact.
  *
  * Citations: ENV = missions/directional_gate/directional_gate_env.py, SENS = epuck/epuck_sensors.py,
  * BEH = epuck/behavior_modules.py, XOR/HOM/FOR/SHL = the mission env files of the reference.
@@ -32,6 +32,13 @@
 typedef struct {
   float x[N], y[N], yaw[N];
 } Pose;
+
+/* Correctly rounded float32 sin/cos/atan2 (evaluate in double, round once).  The reference's SLEEF
+ * kernels agree with these for ~95-98% of arguments and are within 1 ulp otherwise; the CUDA path
+ * uses the same construction so the two pose paths are bit-identical. */
+static inline float cr_sinf(float a) { return (float)sin((double)a); }
+static inline float cr_cosf(float a) { return (float)cos((double)a); }
+static inline float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 
 static inline float signf(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 static inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -264,7 +271,7 @@ static void critic_state(const SwarmParams* p, const Pose* s, float* out /* (N,5
     float hx = rx / norm, hy = ry / norm;
     float ca = hx * 0.0f + hy * 1.0f;
     float sa = hx * 1.0f - hy * 0.0f;
-    float cy = cosf(s->yaw[i]), sy = sinf(s->yaw[i]);
+    float cy = cr_cosf(s->yaw[i]), sy = cr_sinf(s->yaw[i]);
     float cb = cy * hx + sy * hy;
     float sb = hx * sy - hy * cy;
     float* o = out + i * 5;
@@ -275,9 +282,9 @@ static void critic_state(const SwarmParams* p, const Pose* s, float* out /* (N,5
 /* ---- BEH:50-90 ---- */
 static void wheels_from_vector(float dx, float dy, float ms, float* l, float* r) {
   int near_zero = (fabsf(dx) < 1e-5f) && (fabsf(dy) < 1e-5f);
-  float angle = atan2f(dy, dx);
+  float angle = cr_atan2f(dy, dx);
   if (angle < 0.0f) angle = angle + 2.0f * PI_F;
-  float ca = cosf(angle);
+  float ca = cr_cosf(angle);
   int front = angle < PI_F;
   float left = front ? ca : 1.0f, right = front ? 1.0f : ca;
   float mv = fmaxf(fabsf(left), fabsf(right));
@@ -338,8 +345,8 @@ static void dispatch_robot(const SwarmParams* p, int64_t id, const float c[6], f
       steps = dur[id == 4 ? 1 : 2];
       avoiding = 1;
     }
-    float lx = lv * cosf(la), ly = lv * sinf(la);
-    float px = pv * cosf(pa), py = pv * sinf(pa);
+    float lx = lv * cr_cosf(la), ly = lv * cr_sinf(la);
+    float px = pv * cr_cosf(pa), py = pv * cr_sinf(pa);
     float rx, ry;
     if (id == 4) { rx = lx - 0.5f * px; ry = ly - 0.5f * py; }
     else { rx = -lx - 0.5f * px; ry = -ly - 0.5f * py; }
@@ -349,10 +356,10 @@ static void dispatch_robot(const SwarmParams* p, int64_t id, const float c[6], f
     g = (avoiding & 1) | ((steps & 7) << 1) | (enc_dir(dir) << 4);
     w = (w & ~(63 << sh)) | (g << sh);
   } else if (id == 2) { /* BEH:518-545 */
-    float px = pv * cosf(pa), py = pv * sinf(pa);
+    float px = pv * cr_cosf(pa), py = pv * cr_sinf(pa);
     steer(rabx - 0.6f * px, raby - 0.6f * py, ms, &l, &r);
   } else if (id == 3) { /* BEH:547-574 */
-    float px = pv * cosf(pa), py = pv * sinf(pa);
+    float px = pv * cr_cosf(pa), py = pv * cr_sinf(pa);
     steer(-p->alpha * rabx - 0.5f * px, -p->alpha * raby - 0.5f * py, ms, &l, &r);
   }
   *fsm = w;
@@ -369,7 +376,7 @@ typedef struct {
 /* SENS:85-293 */
 static void sense_proximity(const SwarmParams* p, const Pose* s, Sensors* o) {
   for (int i = 0; i < N; ++i) {
-    float cy = cosf(s->yaw[i]), sy = sinf(s->yaw[i]);
+    float cy = cr_cosf(s->yaw[i]), sy = cr_sinf(s->yaw[i]);
     float sum_x = 0.0f, sum_y = 0.0f;
     for (int k = 0; k < 8; ++k) {
       float wdx = p->cos_a[k] * cy - p->sin_a[k] * sy;
@@ -406,7 +413,7 @@ static void sense_proximity(const SwarmParams* p, const Pose* s, Sensors* o) {
     }
     float mag = sqrtf(sum_x * sum_x + sum_y * sum_y);
     o->cache[0][i] = mag > 1.0f ? 1.0f : mag;
-    o->cache[1][i] = atan2f(sum_y, sum_x);
+    o->cache[1][i] = cr_atan2f(sum_y, sum_x);
   }
 }
 
@@ -421,7 +428,7 @@ static void sense_light(const SwarmParams* p, const Pose* s, Sensors* o) {
     float lx = p->light_x - s->x[i], ly = p->light_y - s->y[i];
     float dist = sqrtf(lx * lx + ly * ly + 1e-6f);
     float base = p->light_intensity / (dist / p->unit_scale);
-    float cy = cosf(s->yaw[i]), sy = sinf(s->yaw[i]);
+    float cy = cr_cosf(s->yaw[i]), sy = cr_sinf(s->yaw[i]);
     float nlx = lx / (dist + 1e-8f), nly = ly / (dist + 1e-8f);
     float mx = -INFINITY, sum_x = 0.0f, sum_y = 0.0f;
     for (int k = 0; k < 8; ++k) {
@@ -437,14 +444,14 @@ static void sense_light(const SwarmParams* p, const Pose* s, Sensors* o) {
     }
     int above = mx > p->light_threshold;
     o->cache[2][i] = above ? mx : 0.0f;
-    o->cache[3][i] = above ? atan2f(sum_y, sum_x) : 0.0f;
+    o->cache[3][i] = above ? cr_atan2f(sum_y, sum_x) : 0.0f;
   }
 }
 
 /* SENS:382-501; rab_u is (N,N) for this env */
 static void sense_rab(const SwarmParams* p, const Pose* s, const float* rab_u, Sensors* o) {
   for (int i = 0; i < N; ++i) {
-    float cy = cosf(s->yaw[i]), sy = sinf(s->yaw[i]);
+    float cy = cr_cosf(s->yaw[i]), sy = cr_sinf(s->yaw[i]);
     float n = 0.0f, wx = 0.0f, wy = 0.0f, axs = 0.0f, ays = 0.0f;
     for (int j = 0; j < N; ++j) {
       float dx = s->x[j] - s->x[i], dy = s->y[j] - s->y[i];
@@ -471,8 +478,8 @@ static void sense_rab(const SwarmParams* p, const Pose* s, const float* rab_u, S
       float inv_dist = 1.0f / (dist_units + 1e-8f);
       float bx = dx * cy + dy * sy;
       float by = -dx * sy + dy * cy;
-      float bearing = atan2f(by, bx);
-      float cb = cosf(bearing), sb = sinf(bearing);
+      float bearing = cr_atan2f(by, bx);
+      float cb = cr_cosf(bearing), sb = cr_sinf(bearing);
       wx += inv_dist * cb * inf;
       wy += inv_dist * sb * inf;
       float aw = p->alpha / (1.0f + dist_units);
@@ -669,11 +676,11 @@ int swarm_oracle_step(const SwarmParams* p, const SwarmState* st, const void* ac
       for (int i = 0; i < N; ++i) { /* SENS:592-617 */
         float v = 0.5f * (lw[i] + rw[i]);
         float omega = (rw[i] - lw[i]) / p->wheelbase;
-        float cy = cosf(s.yaw[i]), sy = sinf(s.yaw[i]);
+        float cy = cr_cosf(s.yaw[i]), sy = cr_sinf(s.yaw[i]);
         s.x[i] += v * cy * p->dt;
         s.y[i] += v * sy * p->dt;
         float yw = s.yaw[i] + omega * p->dt;
-        s.yaw[i] = atan2f(sinf(yw), cosf(yw));
+        s.yaw[i] = cr_atan2f(cr_sinf(yw), cr_cosf(yw));
       }
       resolve_walls(p, &s);
       resolve_gate(p, &s);

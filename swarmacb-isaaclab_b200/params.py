@@ -40,6 +40,7 @@ class SwarmParams(C.Structure):
         ("spawn_cx", F), ("spawn_cy", F), ("spawn_sx", F), ("spawn_sy", F), ("spawn_circle_radius", F),
         ("prox_threshold", F),
         ("cos_a", F * 8), ("sin_a", F * 8), ("rab_cos", F * 4), ("rab_sin", F * 4),
+        ("ztilde_lut", F * N),
         ("face_nx", F * 12), ("face_ny", F * 12), ("face_px", F * 12), ("face_py", F * 12),
         ("seg_ax", F * MAX_SEG), ("seg_ay", F * MAX_SEG), ("seg_bx", F * MAX_SEG), ("seg_by", F * MAX_SEG),
         ("seg_sx", F * MAX_SEG), ("seg_sy", F * MAX_SEG),
@@ -171,6 +172,9 @@ def build_params(cfg) -> SwarmParams:
         p.cos_a[k], p.sin_a[k] = float(cos_a[k]), float(sin_a[k])
     for k in range(4):
         p.rab_cos[k], p.rab_sin[k] = float(rab_cos[k]), float(rab_sin[k])
+    zt = 1.0 - 2.0 / (1.0 + torch.exp(torch.arange(N, dtype=torch.float32)))  # SENS:425 on float32 counts
+    for k in range(N):
+        p.ztilde_lut[k] = float(zt[k])
 
     arena = arena_segments(cfg)
     if len(arena) != 12:

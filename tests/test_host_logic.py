@@ -124,9 +124,10 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_oracle():
+    """The product path must not import, link or dlopen anything under oracle/ (comments may name it)."""
     src_dir = os.path.join(ROOT, "swarmacb-isaaclab_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|swarm_oracle|liboracle|oracle/_|#include.*oracle", re.M)
     for dirpath, _, files in os.walk(src_dir):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("no CPU or eager-torch fallback", ""), f
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f
