@@ -29,8 +29,8 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if build_if_missing and _build.needs_build():
+    path = os.environ.get("SWARM_LIB_OVERRIDE") or _build.LIB  # override = tuning variants only
+    if build_if_missing and path == _build.LIB and _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # stale-but-present library is still usable on a box without nvcc

@@ -27,6 +27,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in (SRC, HEADER, __file__))
 
 
+def build_variant(out: str, defines: list[str]) -> str:
+    """Tuning aid: compile csrc/swarm_step.cu with extra -D flags into ``out`` (not used by the product path)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if it is missing or older than its sources; return its path."""
     if not force and not needs_build():
