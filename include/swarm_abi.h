@@ -176,6 +176,11 @@ int swarm_abi_version(void);
 int swarm_kernel_launch_count(void);       /* kernels launched by this library so far */
 const char* swarm_last_error_string(void);
 
+/* Test hook: evaluates include/swarm_detmath.h on the device, sin/cos of a[i] and atan2(a[i], b[i])
+ * (device pointers), so tests can check the device results bit for bit against the host's. */
+int swarm_detmath_eval(const float* a, const float* b, float* sin_a, float* cos_a, float* atan2_ab, int n,
+                       void* stream);
+
 /* FP32 FMA issue-rate micro-benchmark used for the roofline denominator: runs `iters` dependent
  * FMA chains on every SM and returns achieved TFLOP/s in *tflops (synchronises). */
 int swarm_fp32_peak(int iters, float* tflops, void* stream);

@@ -20,7 +20,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    deps = (os.path.join(_HERE, "swarm_oracle.c"), os.path.join(_HERE, "..", "include", "swarm_abi.h"))
+    deps = (os.path.join(_HERE, "swarm_oracle.c"), os.path.join(_HERE, "..", "include", "swarm_abi.h"),
+            os.path.join(_HERE, "..", "include", "swarm_detmath.h"))
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(_LIB_PATH) < os.path.getmtime(d) for d in deps):
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
@@ -130,4 +131,19 @@ def critic_state(params: SwarmParams, state: dict) -> np.ndarray:
     rc = lib().swarm_oracle_critic_state(C.byref(params), C.byref(st), _ptr(out), E)
     if rc != 0:
         raise RuntimeError(f"swarm_oracle_critic_state failed: {rc}")
+    return out
+
+
+def detmath_sincos(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    sn, cs = np.empty_like(a), np.empty_like(a)
+    lib().swarm_oracle_sincos(a.size, _ptr(a), _ptr(sn), _ptr(cs))
+    return sn, cs
+
+
+def detmath_atan2(y: np.ndarray, x: np.ndarray):
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(y)
+    lib().swarm_oracle_atan2(y.size, _ptr(y), _ptr(x), _ptr(out))
     return out

@@ -12,9 +12,10 @@
  * pinned by no reference-owned test.
  *
  * Plain C99, float32 scalar arithmetic in the reference's operation order; build with
- * -ffp-contract=off so no FMA is formed.  sin/cos/atan2 are correctly rounded (double libm, one
- * rounding), the reference's come from SLEEF (<= 1 ulp): last-ulp differences are expected and
- * covered by the stated tolerances (1e-5 m / 1e-5 rad poses, 1e-4 sensors); integer state is exact.
+ * -ffp-contract=off so no FMA is formed outside the explicit fmaf() of include/swarm_detmath.h.
+ * sin/cos/atan2 come from that header (deterministic, <= ~1.5 ulp), the reference's from SLEEF
+ * (<= 1 ulp): last-ulp differences are expected and covered by the stated tolerances (1e-5 m /
+ * 1e-5 rad poses, 1e-4 sensors); integer state is exact.
  *
  * Citations: ENV = missions/directional_gate/directional_gate_env.py, SENS = epuck/epuck_sensors.py,
  * BEH = epuck/behavior_modules.py, XOR/HOM/FOR/SHL = the mission env files of the reference.
@@ -25,6 +26,7 @@
 #include <string.h>
 
 #include "../include/swarm_abi.h"
+#include "../include/swarm_detmath.h"
 
 #define N SWARM_N
 #define PI_F 3.14159265358979323846f
@@ -33,12 +35,12 @@ typedef struct {
   float x[N], y[N], yaw[N];
 } Pose;
 
-/* Correctly rounded float32 sin/cos/atan2 (evaluate in double, round once).  The reference's SLEEF
- * kernels agree with these for ~95-98% of arguments and are within 1 ulp otherwise; the CUDA path
- * uses the same construction so the two pose paths are bit-identical. */
-static inline float cr_sinf(float a) { return (float)sin((double)a); }
-static inline float cr_cosf(float a) { return (float)cos((double)a); }
-static inline float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+/* sin/cos/atan2: the deterministic float32 routines shared with the CUDA kernel
+ * (include/swarm_detmath.h, <= ~1.5 ulp, bit-identical on CPU and GPU); the reference's come from
+ * SLEEF (<= 1 ulp).  tests/test_detmath.py pins them against double-precision libm. */
+static inline float cr_sinf(float a) { float sn, cs; swarm_sincosf(a, &sn, &cs); return sn; }
+static inline float cr_cosf(float a) { float sn, cs; swarm_sincosf(a, &sn, &cs); return cs; }
+static inline float cr_atan2f(float y, float x) { return swarm_atan2f(y, x); }
 
 static inline float signf(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 static inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -754,3 +756,11 @@ int swarm_oracle_critic_state(const SwarmParams* p, const SwarmState* st, float*
 }
 
 int swarm_oracle_abi_version(void) { return SWARM_ABI_VERSION; }
+
+/* test hooks for include/swarm_detmath.h */
+void swarm_oracle_sincos(int n, const float* a, float* sn, float* cs) {
+  for (int i = 0; i < n; ++i) swarm_sincosf(a[i], &sn[i], &cs[i]);
+}
+void swarm_oracle_atan2(int n, const float* y, const float* x, float* out) {
+  for (int i = 0; i < n; ++i) out[i] = swarm_atan2f(y[i], x[i]);
+}

@@ -61,3 +61,23 @@ for line, (e, s, st) in sorted(per_line.items(), key=lambda kv: -kv[1][1])[:top]
     text = src[line - 1].strip()[:70] if line and line <= len(src) else ""
     top_st = ", ".join(f"{k[6:]}:{v}" for k, v in st.most_common(3))
     print(f"L{line!s:>5} inst {100*e/tot_e:5.1f}%  samp {100*s/max(tot_s,1):5.1f}%  [{top_st}]  {text}")
+
+# ---- per-function aggregation (source line ranges) ----
+import bisect
+funcs = []
+for i, t in enumerate(src, 1):
+    m = re.match(r"(?:template\s*<[^>]*>\s*)?__(?:device|global)__.*?\b(\w+)\s*\(", t) or re.match(r"^(\w+)\(const __grid_constant__", t)
+    if m and not t.strip().startswith("//"):
+        funcs.append((i, m.group(1)))
+starts = [f[0] for f in funcs]
+agg = collections.defaultdict(lambda: [0, 0])
+for line, (e, s_, st) in per_line.items():
+    if not line:
+        name = "?"
+    else:
+        k = bisect.bisect_right(starts, line) - 1
+        name = funcs[k][1] if k >= 0 else "?"
+    agg[name][0] += e; agg[name][1] += s_
+print("\nper function: inst%  samp%")
+for name, (e, s_) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print(f"  {name:24s} {100*e/tot_e:5.1f}%  {100*s_/max(tot_s,1):5.1f}%")
