@@ -224,7 +224,7 @@ def measure_workload(torch, name, device, K, W, flush, env_offset_rank, want_e2e
     lib = _lib.load()
     l0 = lib.swarm_kernel_launch_count()
     ms = time_steps(torch, env, actions, K, W, flush)
-    launches = lib.swarm_kernel_launch_count() - l0 - 2 * W
+    launches = lib.swarm_kernel_launch_count() - l0 - W
     res = {"env": env, "E": E, "mission": mission, "mode": mode, "task": task, "idx": idx, "ms": ms,
            "launches": launches, "discrete": discrete}
     if want_e2e:
@@ -371,7 +371,7 @@ def main():
                      "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                      "kernel": "swarm_kernel<FOR,discrete,24,STEP>" if args.workload == "foraging_daisy_16384" else "swarm_kernel",
                      "algorithmic_bytes_per_agent_step": bytes_as,
-                     "timing": "CUDA events around each env.step launch group (memset + any_timeout + swarm_kernel)"},
+                     "timing": "CUDA events around each env.step launch (one swarm_kernel launch per step)"},
         "roofline_fp32": {"bound": "fp32-issue", "achieved": achieved_tf, "peak": float(fp32.value), "unit": "TFLOP/s",
                           "frac": achieved_tf / float(fp32.value) if fp32.value > 0 else None,
                           "algorithmic_flops_per_agent_step": ALG_FLOPS[mission],

@@ -116,7 +116,8 @@ typedef struct SwarmState {
   float* episode_group_reward; /* (E)      ENV:65 */
   float* completed_group_reward;          /* (E)      ENV:64 */
   float* completed_terminal_critic_state; /* (E,N,5)  ENV:69 */
-  int32_t* scratch;            /* >= 4 ints of device scratch (any-reset flag) */
+  int32_t* scratch;            /* >= 4 zero-initialised ints: rotating any-reset flags, slot = step_counter % 3
+                                  (maintained by the kernels; see swarm_sync_episode_flags) */
 } SwarmState;
 
 /* fsm word layout (bits): explore_state[0] explore_steps[1:4] explore_dir[4:6]
@@ -151,6 +152,13 @@ int swarm_step(const SwarmParams* params, const SwarmState* state, const void* a
 /* env.reset(): respawn all E environments and produce the first observation. */
 int swarm_reset(const SwarmParams* params, const SwarmState* state, const SwarmNoise* noise,
                 const SwarmOut* out, int E, void* stream);
+
+/* The reset path re-solves collisions for ALL envs whenever ANY env of the batch times out (ENV:1262).
+ * Each step kernel therefore leaves a flag for the next step (slot (step_counter+1) % 3 of state->scratch).
+ * A caller that rewrites episode_length_buf or scratch itself, or restarts step_counter, must call this
+ * before the next swarm_step so the flag matches the buffer again (swarm_reset does it implicitly). */
+int swarm_sync_episode_flags(const SwarmParams* params, const SwarmState* state, uint64_t next_step_counter,
+                             int E, void* stream);
 
 /* get_critic_state(): (E,N,5) = (rho, cos a, sin a, cos b, sin b). */
 int swarm_critic_state(const SwarmParams* params, const SwarmState* state, float* critic_out,

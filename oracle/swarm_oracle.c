@@ -480,15 +480,26 @@ static void sense_rab(const SwarmParams* p, const Pose* s, const float* rab_u, S
       float inv_dist = 1.0f / (dist_units + 1e-8f);
       float bx = dx * cy + dy * sy;
       float by = -dx * sy + dy * cy;
-      float bearing = cr_atan2f(by, bx);
-      float cb = cr_cosf(bearing), sb = cr_sinf(bearing);
+      /* SENS:438-441 cos/sin(atan2(by, bx)) evaluated as the normalised vector (bx, by)/|(bx, by)| (equal
+       * within 2 ulp, and free of library-dependent transcendentals); coincident robots keep the reference's
+       * atan2-of-signed-zeros bearing (0 or +-float32(pi)). */
+      float nrm2 = bx * bx + by * by, cb, sb;
+      if (nrm2 > 0.0f) {
+        float nrm = sqrtf(nrm2);
+        cb = bx / nrm;
+        sb = by / nrm;
+      } else {
+        float bearing = cr_atan2f(by, bx);
+        cb = cr_cosf(bearing);
+        sb = cr_sinf(bearing);
+      }
       wx += inv_dist * cb * inf;
       wy += inv_dist * sb * inf;
       float aw = p->alpha / (1.0f + dist_units);
       axs += aw * cb * inf;
       ays += aw * sb * inf;
     }
-    o->ztilde[i] = 1.0f - 2.0f / (1.0f + expf(n));
+    o->ztilde[i] = p->ztilde_lut[(int)n]; /* SENS:425 tabulated on the host with the reference's torch ops */
     for (int k = 0; k < 4; ++k) o->rab_proj[i][k] = wx * p->rab_cos[k] + wy * p->rab_sin[k];
     o->cache[4][i] = axs;
     o->cache[5][i] = ays;

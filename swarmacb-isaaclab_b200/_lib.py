@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = (
     "swarm_step", "swarm_reset", "swarm_critic_state", "swarm_rollout", "swarm_host_step",
     "swarm_abi_version", "swarm_kernel_launch_count", "swarm_last_error_string", "swarm_fp32_peak",
-    "swarm_detmath_eval",
+    "swarm_detmath_eval", "swarm_sync_episode_flags",
 )
 
 
@@ -44,6 +44,7 @@ def load(build_if_missing: bool = True):
     lib.swarm_step.argtypes = [P, S, C.c_void_p, Nz, O, C.c_int, C.c_void_p]
     lib.swarm_reset.argtypes = [P, S, Nz, O, C.c_int, C.c_void_p]
     lib.swarm_critic_state.argtypes = [P, S, C.c_void_p, C.c_int, C.c_void_p]
+    lib.swarm_sync_episode_flags.argtypes = [P, S, C.c_uint64, C.c_int, C.c_void_p]
     lib.swarm_rollout.argtypes = [P, S, C.c_void_p, C.c_int64, Nz, O, C.c_int, C.c_int, C.c_void_p]
     lib.swarm_host_step.argtypes = [P, S, C.c_void_p, Nz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, O,
                                     C.c_int, C.c_void_p]

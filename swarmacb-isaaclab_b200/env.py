@@ -98,6 +98,7 @@ class SwarmEnv:
         self._env_offset = int(env_offset)
         self._injected: dict = {}
         self._obs_views = {a: self._obs[:, i] for i, a in enumerate(self.possible_agents)}
+        self._len_version = self.episode_length_buf._version
 
     # ── protocol ────────────────────────────────────────────────────────────────────────────
     @property
@@ -155,6 +156,18 @@ class SwarmEnv:
         self._step_counter += 1
         return nz
 
+    def _sync_flags(self):
+        """Rebuild the kernel's rotating any-reset flags after episode_length_buf was written from outside."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.swarm_sync_episode_flags(C.byref(self.params), C.byref(self._state), self._step_counter,
+                                                    self.num_envs, self._stream())
+        _lib.check(rc, "swarm_sync_episode_flags")
+        self._len_version = self.episode_length_buf._version
+
+    def _check_len_buf(self):
+        if self.episode_length_buf._version != self._len_version:
+            self._sync_flags()
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -195,6 +208,7 @@ class SwarmEnv:
         """One env.step from an (E,N,act) action tensor; returns (obs (E,N,obs), reward (E), time_out (E) bool)
         views of buffers that the next step overwrites."""
         act = self._gather_actions(actions)
+        self._check_len_buf()
         nz = self._noise()
         with torch.cuda.device(self.device):
             rc = self._lib.swarm_step(C.byref(self.params), C.byref(self._state), C.c_void_p(act.data_ptr()),
@@ -225,6 +239,7 @@ class SwarmEnv:
             T, stride = int(steps), 0
         if steps is not None:
             T = int(steps)
+        self._check_len_buf()
         nz = self._noise()
         self._step_counter += T - 1
         with torch.cuda.device(self.device):
@@ -258,6 +273,7 @@ class SwarmEnv:
         }
         for k, dst in m.items():
             dst.copy_(torch.as_tensor(state[k]).to(dst.dtype).reshape(dst.shape))
+        self._sync_flags()
 
     def dump_state(self) -> dict:
         m = {
