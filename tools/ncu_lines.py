@@ -14,9 +14,11 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+HELPER_MAX = int(os.environ.get("HELPER_MAX", "0"))  # attribute lines <= HELPER_MAX (tiny inlined helpers) to their call site
 line_of = {}
 cur_fn, cur_line, active = None, None, False
+chain = []
 for ln in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
     if m:
@@ -25,12 +27,22 @@ for ln in dis.splitlines():
         continue
     if not active:
         continue
-    m = re.search(r'//## File ".*?", line (\d+)(?: inlined at ".*?", line (\d+))?', ln)
+    m = re.search(r'//## File "(.*?)", line (\d+)', ln)
     if m:
-        cur_line = int(m.group(1))
+        chain.append(int(m.group(2)) if m.group(1).endswith("swarm_step.cu") else None)
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S+)", ln)
     if m:
+        pick = None
+        for c in chain:          # innermost first; skip helper-definition lines and other files
+            if c is not None and c > HELPER_MAX:
+                pick = c
+                break
+        if pick is None and chain:
+            pick = chain[0]
+        if chain:
+            cur_line = pick
+        chain = []
         line_of[int(m.group(1), 16)] = (cur_line, m.group(2))
 rows = list(csv.reader(open(sass_csv)))
 # first kernel block only
