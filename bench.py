@@ -141,6 +141,7 @@ def cpu_baseline(mission, mode, budget_s=12.0, E=1024, threads=None):
     from swarmacb_isaaclab_b200 import build_params
     cfg = make_cfg(mission, mode, E, "cpu")
     p = build_params(cfg)
+    cores = oracle.set_threads()
     rng = np.random.default_rng(0)
     host = oracle.new_state(E)
     oracle.reset(p, host, rab_u=rng.random((E, N, N), dtype=np.float32),
@@ -162,7 +163,6 @@ def cpu_baseline(mission, mode, budget_s=12.0, E=1024, threads=None):
         if time.perf_counter() - t0 > budget_s or steps >= 4000:
             break
     dt = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return {"value": E * N * steps / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": f"{E} envs x {steps} steps of {mission}/{mode} (oracle/swarm_oracle.c, OpenMP, noise pre-drawn)",
             "ms_per_step": dt / steps * 1e3}
@@ -180,6 +180,7 @@ def run_reference(args):
     from swarmacb_isaaclab_b200 import build_params
     cfg = make_cfg(mission, mode, E, "cpu")
     p = build_params(cfg)
+    cores = oracle.set_threads()
     rng = np.random.default_rng(0)
     host = oracle.new_state(E)
     noise = dict(rab_u=rng.random((E, N, N), dtype=np.float32), spawn_u=rng.random((8, E, N, 2), dtype=np.float32),
@@ -196,7 +197,6 @@ def run_reference(args):
         oracle.step(p, host, acts[(W + k) % 16], turn_dur=dur, **noise)
     dt = time.perf_counter() - t0
     value = E * N * K / dt
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     sample = f"each step = {E} envs x 20 robots of {task} {mode} (bounded sample of the {E_gpu}-env workload)"
     line = {
         "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s",
@@ -312,22 +312,28 @@ def main():
     e2e_value = agent_steps / e2e_s
 
     # episode-metric reduction: the only collective of the path
+    from swarmacb_isaaclab_b200.sharding import EpisodeMetrics
     env = head["env"]
-    metrics = torch.stack([env._episode_group_reward.sum().double(), env.completed_group_reward.sum().double(),
-                           torch.tensor(float(E * N * K), dtype=torch.float64, device=device)])
-    if world > 1:
-        dist.all_reduce(metrics, op=dist.ReduceOp.SUM)
+    em = EpisodeMetrics(device)
+    em.vec[3] = env._episode_group_reward.sum().double() + env.completed_group_reward.sum().double()
+    em.vec[4] = float(E * N * (K + W))
+    metrics = em.reduce()   # NCCL all-reduce(sum) when world > 1
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
+    peaks, prof = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    try:  # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_metrics.json")))
+    except OSError:
+        pass
+    traffic = prof.get("dram_bytes_per_launch") if args.workload == "foraging_daisy_16384" else None
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     ms_step = total_ms / K
     med_ms = statistics.median(head["ms"])
@@ -368,7 +374,8 @@ def main():
                 "path": "swarm_host_step (C ABI): pinned host actions -> H2D -> step -> obs+reward+time_out D2H, sync"},
         "gpu_launches": head["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": "swarm_kernel<FOR,discrete,24,STEP>" if args.workload == "foraging_daisy_16384" else "swarm_kernel",
                      "algorithmic_bytes_per_agent_step": bytes_as,
                      "timing": "CUDA events around each env.step launch (one swarm_kernel launch per step)"},
@@ -378,8 +385,8 @@ def main():
                           "peak_source": "swarm_fp32_peak FMA micro-benchmark, this run"},
         "ms_per_step_median": med_ms, "ms_per_step_warm_l2": sum(warm) / len(warm),
         "clocks": clocks,
-        "episode_metrics": {"sum_episode_reward": float(metrics[0]), "sum_completed_reward": float(metrics[1]),
-                            "agent_steps": float(metrics[2])},
+        "episode_metrics": {"sum_group_reward": metrics["sum_group_reward"], "agent_steps": metrics["agent_steps"],
+                            "reduced_over_ranks": world},
         "other_workloads": others,
         "cpu_baseline": cpu,
     }

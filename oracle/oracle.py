@@ -147,3 +147,10 @@ def detmath_atan2(y: np.ndarray, x: np.ndarray):
     out = np.empty_like(y)
     lib().swarm_oracle_atan2(y.size, _ptr(y), _ptr(x), _ptr(out))
     return out
+
+
+def set_threads(n: int | None = None) -> int:
+    """Use ``n`` OpenMP threads (default: every core this process may run on); returns the count in effect."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return int(lib().swarm_oracle_set_threads(int(n)))

@@ -21,6 +21,9 @@
  * BEH = epuck/behavior_modules.py, XOR/HOM/FOR/SHL = the mission env files of the reference.
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -767,6 +770,17 @@ int swarm_oracle_critic_state(const SwarmParams* p, const SwarmState* st, float*
 }
 
 int swarm_oracle_abi_version(void) { return SWARM_ABI_VERSION; }
+
+/* number of OpenMP threads the env loops use (torchrun exports OMP_NUM_THREADS=1 by default) */
+int swarm_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 /* test hooks for include/swarm_detmath.h */
 void swarm_oracle_sincos(int n, const float* a, float* sn, float* cs) {
