@@ -97,6 +97,13 @@ typedef struct SwarmParams {
    * XOR/FOR/SHL two circles {c0x,c0y,c1x,c1y,r_sq}; HOM {cx,cy,-,-,r_sq};
    * FOR extra {food_radius, nest_top_y}; SHL extra {left,right,bottom,top} */
   float zone[12];
+  /* --- manual_control.py StandaloneDGTEnv compatibility (BASELINE config 1), used by swarm_mc_tick only ---
+   * MC:531-553 resolves the arena faces one after another (Gauss-Seidel) with r = robot_radius and
+   * face data derived from angles; its 12th face duplicates the west face (mid-angle wraps to pi). */
+  float mc_face_nx[12], mc_face_ny[12], mc_face_px[12], mc_face_py[12];
+  float mc_spawn_safe;       /* MC:251 inradius - 2*robot_radius */
+  float mc_spawn_theta_max;  /* MC:253 pi for Homing, 2*pi otherwise */
+  int32_t mc_mode;           /* 1 when the block above is filled (build_mc_params) */
 } SwarmParams;
 
 /* Persistent per-environment state.  E environments, N = SWARM_N robots. */
@@ -136,6 +143,8 @@ typedef struct SwarmNoise {
   uint64_t seed;           /* Philox key */
   uint64_t step_counter;   /* Philox counter high word; caller increments per step */
   int64_t env_offset;      /* global index of env 0 of this shard (multi-GPU invariance) */
+  const float* rab_u2;     /* (E,N,N) second packet-loss draw of a manual-control tick (MC:435) */
+  const float* mc_spawn_u; /* (E,N,3) radius, angle, yaw draws of MC:252-258 */
 } SwarmNoise;
 
 typedef struct SwarmOut {
@@ -178,6 +187,23 @@ int swarm_host_step(const SwarmParams* params, const SwarmState* state, const vo
                     const SwarmNoise* noise, float* obs_host, float* reward_host,
                     uint8_t* time_out_host, void* dev_actions, const SwarmOut* dev_out, int E,
                     void* stream);
+
+/* One tick of scripts/manual_control.py's loop (MC:721-757) for E standalone environments:
+ *   SWARM_MC_PRE     sensors at the current pose (first RAB draw) + BehaviorModules.dispatch without
+ *                    previous wheels (MC:729-749); robot 0 keeps the wheel command given in `wheels`
+ *   SWARM_MC_PHYSICS StandaloneDGTEnv.step (MC:355-423): clamp in m/s, integrate, one Gauss-Seidel wall
+ *                    pass, one gate pass, one robot pass, mission reward, episode roll-over (MC:753-754)
+ *   SWARM_MC_POST    compute_obs_robot0's sensor pass (second RAB draw, MC:425-440) -> out->obs (E,N,24)
+ * module_ids: int64 (E,N) (needed with PRE); wheels: float (E,N,2) in m/s (robot 0 only with PRE, all
+ * robots without).  params must come from the MC parameter builder (mc_mode == 1). */
+enum { SWARM_MC_PRE = 1, SWARM_MC_PHYSICS = 2, SWARM_MC_POST = 4 };
+int swarm_mc_tick(const SwarmParams* params, const SwarmState* state, const int64_t* module_ids,
+                  const float* wheels, const SwarmNoise* noise, const SwarmOut* out, int flags, int E,
+                  void* stream);
+
+/* MC:245-269 StandaloneDGTEnv.reset(): polar spawn, no collision re-solve. */
+int swarm_mc_reset(const SwarmParams* params, const SwarmState* state, const SwarmNoise* noise, int E,
+                   void* stream);
 
 /* Library / device introspection. */
 int swarm_abi_version(void);

@@ -33,7 +33,8 @@ def lib():
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB_PATH)
-        for name in ("swarm_oracle_step", "swarm_oracle_reset", "swarm_oracle_critic_state"):
+        for name in ("swarm_oracle_step", "swarm_oracle_reset", "swarm_oracle_critic_state", "swarm_oracle_mc_tick",
+                     "swarm_oracle_mc_reset", "swarm_oracle_set_threads"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -154,3 +155,45 @@ def set_threads(n: int | None = None) -> int:
     if n is None:
         n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     return int(lib().swarm_oracle_set_threads(int(n)))
+
+
+MC_PRE, MC_PHYSICS, MC_POST = 1, 2, 4
+
+
+def mc_tick(params: SwarmParams, state: dict, module_ids, wheels, *, rab_u=None, rab_u2=None, turn_dur=None,
+            mc_spawn_u=None, flags=MC_PRE | MC_PHYSICS | MC_POST):
+    """One manual-control tick (scripts/manual_control.py:721-757) on the host; returns (obs24, reward, rolled_over)."""
+    E = state["pos"].shape[0]
+    ids = np.ascontiguousarray(module_ids, dtype=np.int64).reshape(E, N) if module_ids is not None else None
+    wh = np.ascontiguousarray(wheels, dtype=np.float32).reshape(E, N, 2) if wheels is not None else None
+    obs = np.zeros((E, N, 24), np.float32)
+    reward = np.zeros((E,), np.float32)
+    time_out = np.zeros((E,), np.uint8)
+    out = SwarmOut(_ptr(obs), _ptr(reward), _ptr(time_out))
+    st = _state_struct(state)
+    nz, _keep = _noise_struct(E, rab_u, turn_dur, None, None)
+    extra = []
+    if rab_u2 is not None:
+        a = np.ascontiguousarray(rab_u2, dtype=np.float32).reshape(E, N, N)
+        nz.rab_u2 = _ptr(a)
+        extra.append(a)
+    if mc_spawn_u is None:
+        mc_spawn_u = np.zeros((E, N, 3), np.float32)
+    b = np.ascontiguousarray(mc_spawn_u, dtype=np.float32).reshape(E, N, 3)
+    nz.mc_spawn_u = _ptr(b)
+    rc = lib().swarm_oracle_mc_tick(C.byref(params), C.byref(st), _ptr(ids), _ptr(wh), C.byref(nz), C.byref(out),
+                                    int(flags), E)
+    if rc != 0:
+        raise RuntimeError(f"swarm_oracle_mc_tick failed: {rc}")
+    return obs, reward, time_out.astype(bool)
+
+
+def mc_reset(params: SwarmParams, state: dict, mc_spawn_u):
+    E = state["pos"].shape[0]
+    st = _state_struct(state)
+    nz = SwarmNoise()
+    b = np.ascontiguousarray(mc_spawn_u, dtype=np.float32).reshape(E, N, 3)
+    nz.mc_spawn_u = _ptr(b)
+    rc = lib().swarm_oracle_mc_reset(C.byref(params), C.byref(st), C.byref(nz), E)
+    if rc != 0:
+        raise RuntimeError(f"swarm_oracle_mc_reset failed: {rc}")

@@ -618,8 +618,11 @@ static float mission_reward(const SwarmParams* p, const SwarmState* st, int e, c
         int in_food = (fabsf(x - z[0]) <= z[5] && fabsf(y - z[1]) <= z[5]) ||
                       (fabsf(x - z[2]) <= z[5] && fabsf(y - z[3]) <= z[5]);
         int in_nest = y <= z[6];
+        if (p->mc_mode) /* MC:386: the standalone env picks food up on the disc the ground sensor sees */
+          in_food = in_circle(x, y, z[0], z[1], z[4]) || in_circle(x, y, z[2], z[3], z[4]);
         int has_food = (st->mission_flags[e * N + i] & 1) | in_food;
         int arrived = in_nest && has_food;
+        if (p->mc_mode && (st->mission_flags[e * N + i] & 2)) arrived = 0; /* MC:389 ... & ~prev_in_nest */
         if (arrived) { reward += 1.0f; has_food = 0; }
         st->mission_flags[e * N + i] = (uint8_t)(has_food | (in_nest ? 2 : 0));
       }
@@ -770,6 +773,124 @@ int swarm_oracle_critic_state(const SwarmParams* p, const SwarmState* st, float*
 }
 
 int swarm_oracle_abi_version(void) { return SWARM_ABI_VERSION; }
+
+/* ======================= scripts/manual_control.py compatibility (BASELINE config 1) ======================= */
+
+/* MC:531-553: faces one after another (Gauss-Seidel), r = robot_radius, face data derived from angles. */
+static void mc_resolve_walls(const SwarmParams* p, Pose* s) {
+  for (int f = 0; f < 12; ++f) {
+    const float nx = p->mc_face_nx[f], ny = p->mc_face_ny[f];
+    for (int i = 0; i < N; ++i) {
+      float dx = s->x[i] - p->mc_face_px[f];
+      float dy = s->y[i] - p->mc_face_py[f];
+      float sd = dx * nx + dy * ny;
+      float pen = p->robot_radius - sd;
+      if (pen > 0.0f) {
+        s->x[i] += pen * nx;
+        s->y[i] += pen * ny;
+      }
+    }
+  }
+}
+
+/* MC:245-269 */
+static void mc_reset_env(const SwarmParams* p, const SwarmState* st, const SwarmNoise* nz, int e, Pose* s) {
+  for (int i = 0; i < N; ++i) {
+    const float* u = nz->mc_spawn_u + ((size_t)e * N + i) * 3;
+    float r = sqrtf(u[0]) * p->mc_spawn_safe;
+    float th = u[1] * p->mc_spawn_theta_max;
+    s->x[i] = r * cr_cosf(th);
+    s->y[i] = r * cr_sinf(th);
+    if (p->mission == SWARM_HOM) s->y[i] = fabsf(s->y[i]);
+    s->yaw[i] = u[2] * 2.0f * PI_F - PI_F;
+    st->prev_ground[e * N + i] = ground_color(p, s->x[i], s->y[i]);
+    st->fsm[e * N + i] = 0;
+    st->mission_flags[e * N + i] = (uint8_t)((p->mission == SWARM_FOR && s->y[i] <= p->zone[6]) ? 2 : 0);
+  }
+  st->episode_length_buf[e] = 0;
+  st->episode_group_reward[e] = 0.0f;
+}
+
+int swarm_oracle_mc_reset(const SwarmParams* p, const SwarmState* st, const SwarmNoise* nz, int E) {
+  if (!p || !st || !nz || !nz->mc_spawn_u) return SWARM_E_NULL;
+  if (!p->mc_mode) return SWARM_E_PARAM;
+  for (int e = 0; e < E; ++e) {
+    Pose s;
+    mc_reset_env(p, st, nz, e, &s);
+    store_pose(st, e, &s);
+  }
+  return 0;
+}
+
+/* One tick of the manual-control loop, MC:721-757 (see swarm_mc_tick in include/swarm_abi.h). */
+int swarm_oracle_mc_tick(const SwarmParams* p, const SwarmState* st, const int64_t* module_ids, const float* wheels,
+                         const SwarmNoise* nz, const SwarmOut* out, int flags, int E) {
+  if (!p || !st || !nz || !out) return SWARM_E_NULL;
+  if (!p->mc_mode || p->obs_dim != 24) return SWARM_E_PARAM;
+  if ((flags & SWARM_MC_PRE) && (!module_ids || !nz->rab_u || !nz->turn_dur)) return SWARM_E_NULL;
+  if ((flags & SWARM_MC_PHYSICS) && (!wheels || !nz->mc_spawn_u || !out->reward || !out->time_out)) return SWARM_E_NULL;
+  if ((flags & SWARM_MC_POST) && (!nz->rab_u2 || !out->obs)) return SWARM_E_NULL;
+  const float ms = p->max_wheel_speed;
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < E; ++e) {
+    Pose s;
+    load_pose(st, e, &s);
+    float lw[N], rw[N];
+    for (int i = 0; i < N; ++i) {
+      lw[i] = wheels ? wheels[((size_t)e * N + i) * 2] : 0.0f;
+      rw[i] = wheels ? wheels[((size_t)e * N + i) * 2 + 1] : 0.0f;
+    }
+    if (flags & SWARM_MC_PRE) { /* MC:729-749 */
+      Sensors o;
+      sense_proximity(p, &s, &o);
+      sense_light(p, &s, &o);
+      sense_rab(p, &s, nz->rab_u + (size_t)e * N * N, &o);
+      for (int i = 0; i < N; ++i) {
+        float c[6], l, r;
+        for (int k = 0; k < 6; ++k) c[k] = o.cache[k][i];
+        dispatch_robot(p, module_ids[e * N + i], c, 0.0f, 0.0f, nz->turn_dur + ((size_t)e * N + i) * 3,
+                       &st->fsm[e * N + i], &l, &r);
+        if (i > 0) { lw[i] = l; rw[i] = r; } /* robot 0 keeps the keyboard command (MC:725-726, 748-749) */
+      }
+    }
+    if (flags & SWARM_MC_PHYSICS) { /* MC:355-423 */
+      for (int i = 0; i < N; ++i) {
+        float l = clampf(lw[i], -ms, ms), r = clampf(rw[i], -ms, ms);
+        float v = 0.5f * (l + r);
+        float omega = (r - l) / p->wheelbase;
+        float cy = cr_cosf(s.yaw[i]), sy = cr_sinf(s.yaw[i]);
+        s.x[i] += v * cy * p->dt;
+        s.y[i] += v * sy * p->dt;
+        float yw = s.yaw[i] + omega * p->dt;
+        s.yaw[i] = cr_atan2f(cr_sinf(yw), cr_cosf(yw));
+      }
+      mc_resolve_walls(p, &s);
+      resolve_gate(p, &s);
+      resolve_robots(p, &s);
+      int64_t len = st->episode_length_buf[e] + 1;
+      int final_step = len >= p->max_episode_length; /* MC:380 */
+      float reward = mission_reward(p, st, e, &s, final_step);
+      float acc = st->episode_group_reward[e] + reward;
+      out->reward[e] = reward;
+      out->time_out[e] = (uint8_t)final_step;
+      st->episode_group_reward[e] = acc;
+      st->episode_length_buf[e] = len;
+      if (final_step) { /* MC:753-754 reset(advance_episode=True) */
+        st->completed_group_reward[e] = acc;
+        mc_reset_env(p, st, nz, e, &s);
+      }
+    }
+    store_pose(st, e, &s);
+    if (flags & SWARM_MC_POST) { /* MC:425-440 */
+      SwarmNoise nz2 = *nz;
+      nz2.rab_u = nz->rab_u2;
+      SwarmState st2 = *st;
+      st2.beh_cache = NULL; /* compute_obs_robot0 does not feed the behaviour modules */
+      observe_env(p, &st2, &nz2, out, e, &s);
+    }
+  }
+  return 0;
+}
 
 /* number of OpenMP threads the env loops use (torchrun exports OMP_NUM_THREADS=1 by default) */
 int swarm_oracle_set_threads(int n) {

@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = (
     "swarm_step", "swarm_reset", "swarm_critic_state", "swarm_rollout", "swarm_host_step",
     "swarm_abi_version", "swarm_kernel_launch_count", "swarm_last_error_string", "swarm_fp32_peak",
-    "swarm_detmath_eval", "swarm_sync_episode_flags",
+    "swarm_detmath_eval", "swarm_sync_episode_flags", "swarm_mc_tick", "swarm_mc_reset",
 )
 
 
@@ -49,6 +49,8 @@ def load(build_if_missing: bool = True):
     lib.swarm_host_step.argtypes = [P, S, C.c_void_p, Nz, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, O,
                                     C.c_int, C.c_void_p]
     lib.swarm_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_void_p]
+    lib.swarm_mc_tick.argtypes = [P, S, C.c_void_p, C.c_void_p, Nz, O, C.c_int, C.c_int, C.c_void_p]
+    lib.swarm_mc_reset.argtypes = [P, S, Nz, C.c_int, C.c_void_p]
     lib.swarm_detmath_eval.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name).restype = C.c_int

@@ -48,6 +48,8 @@ class SwarmParams(C.Structure):
         ("iw_tx", F * MAX_INTERNAL), ("iw_ty", F * MAX_INTERNAL),
         ("iw_nx", F * MAX_INTERNAL), ("iw_ny", F * MAX_INTERNAL), ("iw_len_sq", F * MAX_INTERNAL),
         ("gate", F * 12), ("zone", F * 12),
+        ("mc_face_nx", F * 12), ("mc_face_ny", F * 12), ("mc_face_px", F * 12), ("mc_face_py", F * 12),
+        ("mc_spawn_safe", F), ("mc_spawn_theta_max", F), ("mc_mode", I),
     ]
 
 
@@ -66,6 +68,7 @@ class SwarmNoise(C.Structure):
     _fields_ = [
         ("rab_u", C.c_void_p), ("turn_dur", C.c_void_p), ("spawn_u", C.c_void_p), ("yaw_u", C.c_void_p),
         ("spawn_rounds", I), ("seed", C.c_uint64), ("step_counter", C.c_uint64), ("env_offset", C.c_int64),
+        ("rab_u2", C.c_void_p), ("mc_spawn_u", C.c_void_p),
     ]
 
 
@@ -235,6 +238,55 @@ def build_params(cfg) -> SwarmParams:
         vals = (c0[0], c0[1], c1[0], c1[1], cfg.black_area_radius ** 2, 0.0, 0.0) + shelter_bounds(cfg)
     for i, v in enumerate(vals):
         p.zone[i] = v
+    return p
+
+
+MC_TASK_MISSION = {
+    "SwarmACB-DirectionalGate-v0": "dgt", "SwarmACB-XOR-v0": "xor", "SwarmACB-Homing-v0": "hom",
+    "SwarmACB-Foraging-v0": "for", "SwarmACB-Sheltering-v0": "shl", "SwarmACB-SCA-v0": "shl", "SwarmACB-SHL-v0": "shl",
+}
+
+
+def build_mc_params(task: str = "SwarmACB-DirectionalGate-v0") -> SwarmParams:
+    """Constants of scripts/manual_control.py's StandaloneDGTEnv (MC:99-210) for ``swarm_mc_tick``.
+
+    Differences from the DirectMARLEnv classes that are reproduced: light at (0,-1.4) (MC:143), nest edge
+    -0.63 (MC:162), no gate push-out for XOR (MC:469-470), arena faces derived from angles and resolved
+    sequentially with r = 0.035 (MC:531-553), episode_steps = round(T/dt) (MC:123), polar spawn (MC:250-258).
+    """
+    from .cfg import MISSION_CFGS
+    mission = MC_TASK_MISSION.get(task, "dgt")  # MC:70-79: unknown tasks fall back to dgt
+    cfg = MISSION_CFGS[mission]()
+    cfg.update_variant("daisy")                 # 24-dim observation (compute_obs_robot0), module-id actions
+    cfg.light_position = (0.0, -1.4, 0.0)
+    if mission == "for":
+        cfg.nest_top_y = -0.63
+    p = build_params(cfg)
+    p.mc_mode = 1
+    p.max_episode_length = int(round(cfg.episode_length_s / 0.1))
+    r, n = 0.035, 12
+    R = math.sqrt(2 * 4.91 / (12 * math.sin(2 * math.pi / 12)))
+    inradius = R * math.cos(math.pi / n)
+    for i in range(n):  # MC:536-544
+        a1 = 2 * math.pi * i / n + math.pi / n
+        a2 = 2 * math.pi * ((i + 1) % n) / n + math.pi / n
+        mid = (a1 + a2) / 2.0
+        p.mc_face_nx[i], p.mc_face_ny[i] = -math.cos(mid), -math.sin(mid)
+        p.mc_face_px[i], p.mc_face_py[i] = inradius * math.cos(mid), inradius * math.sin(mid)
+    p.mc_spawn_safe = inradius - r * 2
+    p.mc_spawn_theta_max = math.pi if mission == "hom" else 2 * math.pi
+    if mission == "xor":
+        p.gate_mode = GATE_NONE
+    if mission == "shl":  # MC:322-329 derives the bounds from float32 tensors
+        half = np.asarray(cfg.shelter_size, dtype=np.float32) / np.float32(2.0)
+        ctr = np.asarray(cfg.shelter_center, dtype=np.float32)
+        left, right = float(ctr[0] - half[0]), float(ctr[0] + half[0])
+        bottom, top = float(ctr[1] - half[1]), float(ctr[1] + half[1])
+        t = cfg.shelter_wall_thickness
+        for i, v in enumerate((left, right, bottom, top, r + t / 2, bottom - r, top + r, left - r, right + r)):
+            p.gate[i] = v
+        for i, v in enumerate((left, right, bottom, top)):
+            p.zone[7 + i] = v
     return p
 
 

@@ -26,7 +26,7 @@ CACHE_FIELDS = ["prox_value", "prox_angle", "light_value", "light_angle", "rab_a
 
 
 def fixture_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("mc_"))
 
 
 def make_cfg(mission: str, mode: str, num_envs: int, decimation: int = 1, device: str = "cpu"):
@@ -167,3 +167,80 @@ def compare(case, params, state, obs, reward, time_out, critic=None, label=""):
         check_float("critic_state", critic, case["critic_state"], 2e-5)
     if errs:
         raise AssertionError(f"[{label}] parity violations:\n  " + "\n  ".join(errs))
+
+
+# ── manual_control.py (BASELINE config 1) rollouts ─────────────────────────────────────────────
+MC_FSM = ["_explore_state", "_explore_steps", "_explore_dir", "_photo_avoiding", "_photo_steps", "_photo_dir",
+          "_antiphoto_avoiding", "_antiphoto_steps", "_antiphoto_dir"]
+
+
+def mc_fixture_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "mc_*.npz")))
+
+
+class McFixture:
+    """Tick-by-tick record of the reference's StandaloneDGTEnv loop (tests/golden/gen_golden_mc.py), E = 1."""
+
+    def __init__(self, path):
+        from swarmacb_isaaclab_b200.params import build_mc_params
+        z = np.load(path)
+        self.name = os.path.basename(path)[:-4]
+        self.meta = json.loads(str(z["meta"]))
+        self.z = {k: z[k] for k in z.files if k != "meta"}
+        self.ticks = self.meta["ticks"]
+        self.params = build_mc_params(self.meta["task"])
+        assert self.params.max_episode_length == self.meta["episode_steps"]
+        unpack = lambda a: np.unpackbits(a, axis=1)[:, : N * N].reshape(self.ticks, 1, N, N).astype(bool)
+        self.keep1, self.keep2 = unpack(self.z["rab_keep1"]), unpack(self.z["rab_keep2"])
+
+    def state(self, t):
+        """State BEFORE tick t (ABI layouts, E=1)."""
+        z = self.z
+        g = (lambda k: z["init_" + k]) if t == 0 else (lambda k: z["post_" + k][t - 1])
+        fsm = pack_fsm(*[torch.from_numpy(np.ascontiguousarray(g("fsm" + f))) for f in MC_FSM]).numpy().astype(np.int32)
+        return {
+            "pos": g("pos").astype(np.float32)[None], "yaw": g("yaw").astype(np.float32)[None],
+            "prev_ground": g("prev_ground").astype(np.float32)[None],
+            "cached_left": np.zeros((1, N), np.float32), "cached_right": np.zeros((1, N), np.float32),
+            "fsm": fsm[None], "beh_cache": np.zeros((1, 6, N), np.float32),
+            "mission_flags": (g("has_food").astype(np.uint8) | (g("prev_in_nest").astype(np.uint8) << 1))[None],
+            "episode_length_buf": np.array([g("step_count")], np.int64),
+            "episode_group_reward": np.array([g("episode_reward")], np.float32),
+            "completed_group_reward": np.zeros(1, np.float32),
+            "completed_terminal_critic_state": np.zeros((1, N, 5), np.float32),
+        }
+
+    def tick_inputs(self, t):
+        z = self.z
+        p_loss = float(self.params.rab_loss_probability)
+        u = lambda keep: np.where(keep, np.float32(min(1.0, p_loss + 0.05)), np.float32(p_loss * 0.5)).astype(np.float32)
+        wheels = np.zeros((1, N, 2), np.float32)
+        wheels[0, 0] = z["wheels0"][t]
+        return dict(module_ids=z["module_ids"][t][None].astype(np.int64), wheels=wheels, rab_u=u(self.keep1[t]),
+                    rab_u2=u(self.keep2[t]), turn_dur=z["turn_dur"][t][None].astype(np.int32),
+                    mc_spawn_u=z["mc_spawn_u"][t][None].astype(np.float32))
+
+    def check(self, t, state, obs, reward, rolled, label=""):
+        z, want = self.z, self.state(t + 1)
+        errs = []
+        d = np.abs(state["pos"] - want["pos"]).max()
+        if not d <= POS_TOL:
+            errs.append(f"pos {d:.3e}")
+        d = angle_diff(state["yaw"], want["yaw"]).max()
+        if not d <= YAW_TOL:
+            errs.append(f"yaw {d:.3e}")
+        keys = ["fsm", "prev_ground", "episode_length_buf", "episode_group_reward"]
+        if self.params.mission == 3:  # has_food / prev_in_nest only mean something in Foraging (MC:385-392)
+            keys.append("mission_flags")
+        for k in keys:
+            if not np.array_equal(state[k], want[k]):
+                errs.append(f"{k} mismatch: got {state[k].ravel()[:6]} want {want[k].ravel()[:6]}")
+        if float(reward[0]) != float(z["reward"][t]):
+            errs.append(f"reward {reward[0]} != {z['reward'][t]}")
+        if bool(rolled[0]) != bool(z["rolled"][t]):
+            errs.append("episode roll-over flag")
+        d = np.abs(obs[0, 0] - z["obs0"][t]).max()
+        if not d <= SENSOR_TOL:
+            errs.append(f"obs robot0 {d:.3e}")
+        if errs:
+            raise AssertionError(f"[{label} tick {t}] " + "; ".join(errs))
