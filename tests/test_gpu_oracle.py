@@ -223,3 +223,28 @@ def test_free_running_timeouts_match_oracle(mission, mode):
         if p.discrete_actions:
             assert np.array_equal(dev["fsm"], host["fsm"]) and np.array_equal(dev["beh_cache"], host["beh_cache"])
     assert resets >= 2 * E
+
+
+@pytest.mark.parametrize("E", [1, 5, 17, 33])
+def test_ragged_batch_sizes(E):
+    """Batches that do not fill a 16-warp block (tail warps shadow the last env without stores)."""
+    env = _mk("shl", "daisy", E)
+    p = env.params
+    rng = np.random.default_rng(E)
+    host = oracle.new_state(E)
+    guard = torch.full((E + 2, N, 24), 7.0, device="cuda:0")          # canaries around the obs buffer
+    noise = dict(rab_u=rng.random((E, N, N), dtype=np.float32), spawn_u=_cluster(rng, E), yaw_u=rng.random((E, N), dtype=np.float32))
+    env.inject_noise(**noise)
+    env.reset()
+    oracle.reset(p, host, **noise)
+    for t in range(4):
+        act = rng.integers(0, 6, (E, N), dtype=np.int64)
+        noise = dict(rab_u=rng.random((E, N, N), dtype=np.float32), turn_dur=rng.integers(1, 5, (E, N, 3)).astype(np.int32))
+        env.inject_noise(**noise)
+        obs, rew, to = env.step_tensor(torch.as_tensor(act, device="cuda:0"))
+        obs_o, rew_o, _ = oracle.step(p, host, act, **noise)
+        torch.cuda.synchronize()
+        dev = env.dump_state()
+        assert np.array_equal(dev["pos"], host["pos"]) and np.array_equal(obs.cpu().numpy(), obs_o)
+        assert np.array_equal(rew.cpu().numpy(), rew_o)
+    assert (guard == 7.0).all()

@@ -131,3 +131,51 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def _lib_no_gpu():
+    from swarmacb_isaaclab_b200 import _lib
+    return _lib.load()
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Argument validation runs before any CUDA call, so the error contract is testable without a GPU:
+    0 ok, <0 SWARM_E_* (-> ValueError in the Python mirror), >0 cudaError_t (-> RuntimeError)."""
+    lib = _lib_no_gpu()
+    p = P.build_params(pkg.HomingEnvCfg())
+    st, nz, out = P.SwarmState(), P.SwarmNoise(), P.SwarmOut()
+    C = ctypes
+    assert lib.swarm_step(None, C.byref(st), None, C.byref(nz), C.byref(out), 4, None) == -1          # SWARM_E_NULL
+    assert lib.swarm_step(C.byref(p), C.byref(st), None, C.byref(nz), C.byref(out), 0, None) == -3    # SWARM_E_SIZE
+    bad = P.build_params(pkg.HomingEnvCfg())
+    bad.abi_version = 99
+    assert lib.swarm_step(C.byref(bad), C.byref(st), None, C.byref(nz), C.byref(out), 4, None) == -4  # SWARM_E_VERSION
+    bad = P.build_params(pkg.HomingEnvCfg())
+    bad.obs_dim = 7
+    assert lib.swarm_step(C.byref(bad), C.byref(st), None, C.byref(nz), C.byref(out), 4, None) == -2  # SWARM_E_PARAM
+    bad = P.build_params(pkg.HomingEnvCfg())
+    bad.gate_mode = P.GATE_SHL
+    assert lib.swarm_reset(C.byref(bad), C.byref(st), C.byref(nz), C.byref(out), 4, None) == -2
+    assert lib.swarm_step(C.byref(p), C.byref(st), None, C.byref(nz), C.byref(out), 4, None) == -1    # null state ptrs
+    assert b"null" in lib.swarm_last_error_string()
+    assert lib.swarm_critic_state(C.byref(p), C.byref(st), None, 4, None) == -1
+    assert lib.swarm_mc_tick(C.byref(p), C.byref(st), None, None, C.byref(nz), C.byref(out), 7, 1, None) == -2  # not MC params
+    mc = P.build_mc_params("SwarmACB-XOR-v0")
+    assert lib.swarm_mc_tick(C.byref(mc), C.byref(st), None, None, C.byref(nz), C.byref(out), 0, 1, None) == -2  # empty flags
+    assert lib.swarm_rollout(C.byref(p), C.byref(st), None, 0, C.byref(nz), C.byref(out), 4, 5, None) == -1
+    from swarmacb_isaaclab_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.check(-2, "x")
+    with pytest.raises(RuntimeError):
+        _lib.check(700, "x")
+
+
+def test_mc_params_reproduce_reference_quirks():
+    mc = P.build_mc_params("SwarmACB-XOR-v0")
+    assert mc.mc_mode == 1 and mc.gate_mode == P.GATE_NONE and mc.max_episode_length == 1800
+    assert mc.light_y == pytest.approx(-1.4)
+    # manual_control.py:536-544: the 12th face's mid-angle wraps to pi -> duplicate of the west face
+    assert mc.mc_face_nx[11] == pytest.approx(1.0) and mc.mc_face_px[11] == pytest.approx(mc.mc_face_px[5])
+    assert P.build_mc_params("SwarmACB-Foraging-v0").zone[6] == pytest.approx(-0.63)
+    assert P.build_mc_params("SwarmACB-Homing-v0").mc_spawn_theta_max == pytest.approx(math.pi)
+    assert P.build_mc_params("nonsense").mission == P.MISSION_ID["dgt"]
