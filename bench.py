@@ -233,16 +233,9 @@ def measure_workload(torch, name, device, K, W, flush, env_offset_rank, want_e2e
         h_obs = torch.empty(E, N, env.obs_dim, dtype=torch.float32).pin_memory()
         h_rew = torch.empty(E, dtype=torch.float32).pin_memory()
         h_to = torch.empty(E, dtype=torch.uint8).pin_memory()
-        d_act = torch.empty_like(actions[0])
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
         def host_step(t):
-            nz = env._noise()
-            rc = lib.swarm_host_step(C.byref(env.params), C.byref(env._state), C.c_void_p(h_act[t % T].data_ptr()),
-                                     C.byref(nz), C.c_void_p(h_obs.data_ptr()), C.c_void_p(h_rew.data_ptr()),
-                                     C.c_void_p(h_to.data_ptr()), C.c_void_p(d_act.data_ptr()), C.byref(env._out),
-                                     E, stream)
-            _lib.check(rc, "swarm_host_step")
+            env.step_host(h_act[t % T], h_obs, h_rew, h_to)
 
         for w in range(W):
             host_step(w)
@@ -371,7 +364,8 @@ def main():
         },
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": head["h2d"],
                 "d2h_bytes_per_step": head["d2h"],
-                "path": "swarm_host_step (C ABI): pinned host actions -> H2D -> step -> obs+reward+time_out D2H, sync"},
+                "path": "SwarmEnv.step_host -> swarm_host_step (C ABI): pinned host actions H2D, step, obs+reward+time_out D2H "
+                        "into pinned host buffers, 8 env chunks pipelined over a copy stream, stream sync"},
         "gpu_launches": head["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,

@@ -248,6 +248,29 @@ class SwarmEnv:
         _lib.check(rc, "swarm_rollout")
         return self._obs, self._reward, self._time_out.view(torch.bool)
 
+    def step_host(self, actions_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
+                  time_out_host: torch.Tensor):
+        """One env.step for a caller whose buffers live in (pinned) HOST memory: ``swarm_host_step`` uploads the
+        (E,N,act) action batch, steps, and downloads obs (E,N,obs) / reward (E) / time_out (E) uint8 into the given
+        host tensors, chunked so the PCIe copies overlap the kernel.  Returns after the results have landed."""
+        want = torch.long if self.params.discrete_actions else torch.float32
+        E = self.num_envs
+        for name, t, dt, numel in (("actions_host", actions_host, want, E * N * self.act_dim),
+                                   ("obs_host", obs_host, torch.float32, E * N * self.obs_dim),
+                                   ("reward_host", reward_host, torch.float32, E),
+                                   ("time_out_host", time_out_host, torch.uint8, E)):
+            if t.device.type != "cpu" or t.dtype != dt or t.numel() != numel or not t.is_contiguous():
+                raise ValueError(f"step_host: {name} must be a contiguous CPU {dt} tensor with {numel} elements")
+        self._check_len_buf()
+        nz = self._noise()
+        with torch.cuda.device(self.device):
+            rc = self._lib.swarm_host_step(C.byref(self.params), C.byref(self._state), C.c_void_p(actions_host.data_ptr()),
+                                           C.byref(nz), C.c_void_p(obs_host.data_ptr()), C.c_void_p(reward_host.data_ptr()),
+                                           C.c_void_p(time_out_host.data_ptr()), C.c_void_p(self._act_buf.data_ptr()),
+                                           C.byref(self._out), E, self._stream())
+        _lib.check(rc, "swarm_host_step")
+        return obs_host, reward_host, time_out_host
+
     def get_critic_state(self) -> torch.Tensor:
         """(E,N,5) = (rho, cos alpha, sin alpha, cos beta, sin beta), ENV:1279-1290."""
         out = torch.empty(self.num_envs, N, 5, dtype=torch.float32, device=self.device)

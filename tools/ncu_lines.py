@@ -69,7 +69,8 @@ for r in body:
             pl[2][hdr[i]] += v
 src = open(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "swarm_step.cu")).read().splitlines()
 print(f"total warp-instr {tot_e}  samples {tot_s}  sass instrs {len(body)}")
-for line, (e, s, st) in sorted(per_line.items(), key=lambda kv: -kv[1][1])[:top]:
+SORT = 0 if os.environ.get("SORT", "samples") == "inst" else 1
+for line, (e, s, st) in sorted(per_line.items(), key=lambda kv: -kv[1][SORT])[:top]:
     text = src[line - 1].strip()[:70] if line and line <= len(src) else ""
     top_st = ", ".join(f"{k[6:]}:{v}" for k, v in st.most_common(3))
     print(f"L{line!s:>5} inst {100*e/tot_e:5.1f}%  samp {100*s/max(tot_s,1):5.1f}%  [{top_st}]  {text}")
