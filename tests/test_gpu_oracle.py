@@ -281,3 +281,60 @@ def test_host_buffer_step_equals_device_step(mission, mode, E):
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
     assert rolled == len(range(0, E, 5))
+
+
+@pytest.mark.parametrize("mission,mode,dec,T,repeat", [
+    ("for", "daisy", 1, 5, True), ("for", "daisy", 1, 7, False), ("hom", "lily", 1, 5, True),
+    ("dgt", "dandelion", 1, 5, True), ("shl", "oc2", 1, 37, False), ("xor", "cyclamen", 2, 6, False),
+    ("shl", "oc2c", 1, 5, True), ("dgt", "daisy", 1, 33, True),
+])
+@pytest.mark.parametrize("fuse_discrete", [True, False])
+def test_fused_rollout_equals_single_steps(mission, mode, dec, T, repeat, fuse_discrete, monkeypatch):
+    """swarm_rollout (T env.steps fused in one launch, state in registers, sensors skipped where nothing reads
+    them) must leave exactly the state, last observation, summed reward and OR-ed time_out of T swarm_step
+    calls on the same Philox stream - including envs that roll over inside the window, the all-env re-solve
+    they trigger, and the single steps that follow the rollout (rotating any-reset flags rebuilt)."""
+    if fuse_discrete:   # exercise the fused kernel for the module-action variants too (default: back-to-back launches)
+        monkeypatch.setenv("SWARM_FUSE_DISCRETE", "1")
+    else:
+        monkeypatch.delenv("SWARM_FUSE_DISCRETE", raising=False)
+    E = 600
+    a, b = _mk(mission, mode, E, dec), _mk(mission, mode, E, dec)
+    a.reset(seed=11)
+    b.reset(seed=11)
+    L = a.max_episode_length
+    for env in (a, b):   # roll-overs at different steps of the window; some envs untouched
+        env.episode_length_buf[::7] = L - 2
+        env.episode_length_buf[3::13] = L - 4
+        env.episode_length_buf[5::17] = L - 1
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    discrete = bool(a.params.discrete_actions)
+    n_act = 1 if repeat else T
+    if discrete:
+        acts = torch.randint(0, 6, (n_act, E, N, 1), generator=g, device="cuda:0")
+    else:
+        acts = torch.rand(n_act, E, N, 2, generator=g, device="cuda:0") * 2.4 - 1.2
+    rew = torch.zeros(E, device="cuda:0")
+    to = torch.zeros(E, dtype=torch.bool, device="cuda:0")
+    for t in range(T):
+        obs_a, r, d = a.step_tensor(acts[0 if repeat else t])
+        rew += r
+        to |= d
+    obs_b, rew_b, to_b = b.rollout(acts[0] if repeat else acts, T)
+    assert torch.equal(obs_a, obs_b), "last observation differs"
+    assert torch.equal(rew, rew_b) and torch.equal(to, to_b)
+    assert int(to.sum()) >= len(range(0, E, 7))
+    sa, sb = a.dump_state(), b.dump_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert torch.equal(a.get_critic_state(), b.get_critic_state())
+    # single steps after the rollout: flags, counters and Philox stream continue identically
+    b.episode_length_buf[1::19] = L - 2
+    a.episode_length_buf[1::19] = L - 2
+    for t in range(3):
+        oa, ra, da = a.step_tensor(acts[0])
+        ob, rb, db = b.step_tensor(acts[0])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"post-rollout step {t}"
+    sa, sb = a.dump_state(), b.dump_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
