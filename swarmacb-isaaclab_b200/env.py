@@ -41,14 +41,8 @@ class SwarmEnv:
             cfg = DirectionalGateEnvCfg()
         self.cfg = cfg
         self.render_mode = render_mode
-        self.device = torch.device(cfg.sim.device)
-        if self.device.type != "cuda" or not torch.cuda.is_available():
-            raise RuntimeError(
-                "SwarmEnv runs only on a CUDA device (the fused sm_100a step has no CPU fallback); "
-                f"cfg.sim.device={cfg.sim.device!r}, torch.cuda.is_available()={torch.cuda.is_available()}")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        self._lib = _lib.load()
+        self.device = self._resolve_device(cfg.sim.device)
+        self._lib = self._load_library()
         self.params = build_params(cfg)
         self.num_envs = int(cfg.scene.num_envs)
         self.scene = types.SimpleNamespace(num_envs=self.num_envs)
@@ -99,6 +93,24 @@ class SwarmEnv:
         self._injected: dict = {}
         self._obs_views = {a: self._obs[:, i] for i, a in enumerate(self.possible_agents)}
         self._len_version = self.episode_length_buf._version
+
+    # ── device / library binding ────────────────────────────────────────────────────────────
+    def _resolve_device(self, name) -> torch.device:
+        """The step exists only as the CUDA kernel: anything but a usable CUDA device is an error."""
+        device = torch.device(name)
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError(
+                "SwarmEnv runs only on a CUDA device (the fused sm_100a step has no CPU fallback); "
+                f"cfg.sim.device={name!r}, torch.cuda.is_available()={torch.cuda.is_available()}")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return device
+
+    def _load_library(self):
+        return _lib.load()  # raises SwarmLibraryError when libswarmstep.so is missing
+
+    def _device_guard(self):
+        return torch.cuda.device(self.device)
 
     # ── protocol ────────────────────────────────────────────────────────────────────────────
     @property
@@ -158,7 +170,7 @@ class SwarmEnv:
 
     def _sync_flags(self):
         """Rebuild the kernel's rotating any-reset flags after episode_length_buf was written from outside."""
-        with torch.cuda.device(self.device):
+        with self._device_guard():
             rc = self._lib.swarm_sync_episode_flags(C.byref(self.params), C.byref(self._state), self._step_counter,
                                                     self.num_envs, self._stream())
         _lib.check(rc, "swarm_sync_episode_flags")
@@ -175,7 +187,7 @@ class SwarmEnv:
         if seed is not None:
             self._seed = int(seed)
         nz = self._noise()
-        with torch.cuda.device(self.device):
+        with self._device_guard():
             rc = self._lib.swarm_reset(C.byref(self.params), C.byref(self._state), C.byref(nz), C.byref(self._out),
                                        self.num_envs, self._stream())
         _lib.check(rc, "swarm_reset")
@@ -210,7 +222,7 @@ class SwarmEnv:
         act = self._gather_actions(actions)
         self._check_len_buf()
         nz = self._noise()
-        with torch.cuda.device(self.device):
+        with self._device_guard():
             rc = self._lib.swarm_step(C.byref(self.params), C.byref(self._state), C.c_void_p(act.data_ptr()),
                                       C.byref(nz), C.byref(self._out), self.num_envs, self._stream())
         _lib.check(rc, "swarm_step")
@@ -242,7 +254,7 @@ class SwarmEnv:
         self._check_len_buf()
         nz = self._noise()
         self._step_counter += T - 1
-        with torch.cuda.device(self.device):
+        with self._device_guard():
             rc = self._lib.swarm_rollout(C.byref(self.params), C.byref(self._state), C.c_void_p(actions.data_ptr()),
                                          stride, C.byref(nz), C.byref(self._out), E, T, self._stream())
         _lib.check(rc, "swarm_rollout")
@@ -263,7 +275,7 @@ class SwarmEnv:
                 raise ValueError(f"step_host: {name} must be a contiguous CPU {dt} tensor with {numel} elements")
         self._check_len_buf()
         nz = self._noise()
-        with torch.cuda.device(self.device):
+        with self._device_guard():
             rc = self._lib.swarm_host_step(C.byref(self.params), C.byref(self._state), C.c_void_p(actions_host.data_ptr()),
                                            C.byref(nz), C.c_void_p(obs_host.data_ptr()), C.c_void_p(reward_host.data_ptr()),
                                            C.c_void_p(time_out_host.data_ptr()), C.c_void_p(self._act_buf.data_ptr()),
@@ -274,7 +286,7 @@ class SwarmEnv:
     def get_critic_state(self) -> torch.Tensor:
         """(E,N,5) = (rho, cos alpha, sin alpha, cos beta, sin beta), ENV:1279-1290."""
         out = torch.empty(self.num_envs, N, 5, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._device_guard():
             rc = self._lib.swarm_critic_state(C.byref(self.params), C.byref(self._state), C.c_void_p(out.data_ptr()),
                                               self.num_envs, self._stream())
         _lib.check(rc, "swarm_critic_state")

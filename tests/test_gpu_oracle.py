@@ -338,3 +338,17 @@ def test_fused_rollout_equals_single_steps(mission, mode, dec, T, repeat, fuse_d
     sa, sb = a.dump_state(), b.dump_state()
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
+
+
+def test_headless_runner_random_policy(tmp_path, capsys):
+    """`python -m swarmacb_isaaclab_b200.runner --config X.yaml` without a reference checkout: random policy at the
+    trainers' cadence through SwarmEnv.rollout, one JSON line of throughput and episode metrics."""
+    import json
+    from swarmacb_isaaclab_b200 import runner
+    path = tmp_path / "run.yaml"
+    path.write_text("behaviors:\n  DirGate_dandelion:\n    task: SwarmACB-DirectionalGate-v0\n    variant: dandelion\n"
+                    "    environment:\n      num_envs: 256\n      decision_period: 5\n      episode_length_s: 3.0\n")
+    assert runner.main(["--config", str(path), "--decisions", "12", "--seed", "2"]) == 0
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert out["envs"] == 256 and out["env_steps"] == 60 and out["obs_dim"] == 24 and not out["discrete_actions"]
+    assert out["episodes_finished"] == 256 * 2 and out["agent_steps_per_s"] > 0

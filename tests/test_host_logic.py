@@ -179,3 +179,42 @@ def test_mc_params_reproduce_reference_quirks():
     assert P.build_mc_params("SwarmACB-Foraging-v0").zone[6] == pytest.approx(-0.63)
     assert P.build_mc_params("SwarmACB-Homing-v0").mc_spawn_theta_max == pytest.approx(math.pi)
     assert P.build_mc_params("nonsense").mission == P.MISSION_ID["dgt"]
+
+
+_RUN_YAML = """
+behaviors:
+  OC2_Sheltering_cyclamen:
+    task: SwarmACB-Sheltering-v0
+    variant: cyclamen
+    trainer_type: oc2
+    max_steps: 1000
+    time_horizon: 40
+    environment:
+      num_envs: 7
+      decision_period: 4
+      episode_length_s: 12.0
+      no_such_key: 1
+"""
+
+
+def test_runner_builds_env_cfg_like_train_py(tmp_path):
+    """runner.load_run_spec / build_env_cfg follow agents/config_loader.py:30-187 and scripts/train.py:166-185."""
+    from swarmacb_isaaclab_b200 import ShelteringEnvCfg, runner
+    path = tmp_path / "run.yaml"
+    path.write_text(_RUN_YAML)
+    spec = runner.load_run_spec(str(path))
+    assert (spec.run_name, spec.task_id, spec.variant) == ("OC2_Sheltering_cyclamen", "SwarmACB-Sheltering-v0", "cyclamen")
+    assert spec.trainer_type == "learned_option_critic" and spec.decision_period == 4
+    assert spec.env_overrides == {"num_envs": 7, "episode_length_s": 12.0, "no_such_key": 1}
+    warned = []
+    cfg = runner.build_env_cfg(spec.task_id, spec.variant, spec.trainer_type, spec.env_overrides, seed=3,
+                               device="cuda:0", warn=warned.append)
+    assert isinstance(cfg, ShelteringEnvCfg) and cfg.scene.num_envs == 7 and cfg.episode_length_s == 12.0
+    assert cfg.seed == 3 and not cfg.discrete_actions and cfg.full_policy_observations   # CFG:195-209
+    assert len(warned) == 1 and "no_such_key" in warned[0]
+    with pytest.raises(KeyError):
+        runner.build_env_cfg("SwarmACB-Nope-v0", "lily")
+    with pytest.raises(FileNotFoundError):
+        runner.load_run_spec(str(tmp_path / "missing.yaml"))
+    with pytest.raises(FileNotFoundError):
+        runner.import_reference_agents(str(tmp_path))
