@@ -9,11 +9,12 @@ import bisect, collections, os, re, subprocess, sys, tempfile
 
 so, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+HELPER_MAX = int(os.environ.get("HELPER_MAX", "0"))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-src_path = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "swarm_step.cu")
+src_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "swarmacb-isaaclab_b200", "csrc", "swarm_step.cu")
 src = open(src_path).read().splitlines()
 per_line = collections.Counter()
 ops = collections.Counter()
@@ -35,6 +36,11 @@ for ln in dis.splitlines():
     if m:
         if chain:
             cur = chain[0]
+            if HELPER_MAX:   # attribute tiny helpers (fadd/fdiv/... defined above line HELPER_MAX) to their call site
+                for c in chain:
+                    if c[0] == "swarm_step.cu" and c[1] > HELPER_MAX:
+                        cur = c
+                        break
         chain = []
         per_line[cur] += 1
         ops[m.group(2).split(".")[0]] += 1
