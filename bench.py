@@ -134,6 +134,24 @@ def time_steps(torch, env, actions, K, W, flush):
     return [s.elapsed_time(e) for s, e in zip(starts, stops)]
 
 
+def time_rollouts(torch, env, T, reps, flush):
+    """Mean ms of one decision = SwarmEnv.rollout(action, T) with a fresh random action per decision (L2 flushed)."""
+    E = env.num_envs
+    acts = gen_actions(torch, bool(env.params.discrete_actions), 16, E, env.device, seed=3)
+    for w in range(3):
+        env.rollout(acts[w], T)
+    ms = []
+    for k in range(reps):
+        flush.add_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        env.rollout(acts[k % 16], T)
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return sum(ms) / len(ms)
+
+
 def cpu_baseline(mission, mode, budget_s=12.0, E=1024, threads=None):
     """The oracle port (oracle/swarm_oracle.c, OpenMP over envs) timed on this host's cores on a bounded
     sample of the same workload: E envs x as many steps as fit the budget."""
@@ -341,13 +359,21 @@ def main():
 
     others = {}
     if not args.no_others:
-        for name in ("homing_lily_4096", "dirgate_dandelion_8192", "sheltering_oc2_16384"):
+        for name in ("homing_lily_4096", "dirgate_dandelion_8192", "sheltering_oc2_16384", "xor_cyclamen_16384"):
             if name == args.workload:
                 continue
             r = measure_workload(torch, name, device, min(K, 100), 5, flush, 0, want_e2e=False)
             m = sum(r["ms"]) / len(r["ms"])
             others[name] = {"value": r["E"] * N / (m * 1e-3), "unit": "agent-steps/s (1 GPU)", "ms_per_step": m,
-                            "config": f"BASELINE.json configs[{r['idx']}]"}
+                            "config": f"BASELINE.json configs[{r['idx']}]" if r["idx"] else
+                                      "XOR env of configs[0] at the headline batch size"}
+            # the trainers' cadence (one action held for decision_period=5 motion updates, agents/poca_trainer.py:564-573)
+            # through SwarmEnv.rollout: one fused launch for wheel actions, 5 back-to-back launches for module actions
+            m5 = time_rollouts(torch, r["env"], 5, min(K, 60), flush)
+            others[name]["decision_period_5"] = {"value": r["E"] * N * 5 / (m5 * 1e-3), "unit": "agent-steps/s (1 GPU)",
+                                                 "ms_per_decision": m5,
+                                                 "path": "swarm_rollout, fused kernel" if not r["discrete"] else
+                                                         "swarm_rollout, 5 launches"}
 
     cpu = None if args.no_cpu else cpu_baseline(mission, head["mode"])
 
