@@ -123,8 +123,9 @@ typedef struct SwarmState {
   float* episode_group_reward; /* (E)      ENV:65 */
   float* completed_group_reward;          /* (E)      ENV:64 */
   float* completed_terminal_critic_state; /* (E,N,5)  ENV:69 */
-  int32_t* scratch;            /* >= 4 zero-initialised ints: rotating any-reset flags, slot = step_counter % 3
-                                  (maintained by the kernels; see swarm_sync_episode_flags) */
+  int32_t* scratch;            /* >= 4 zero-initialised ints: [0..2] rotating any-reset flags, slot = step_counter % 3
+                                  (maintained by the kernels; see swarm_sync_episode_flags); [3] per-step reset
+                                  mask of a fused swarm_rollout */
 } SwarmState;
 
 /* fsm word layout (bits): explore_state[0] explore_steps[1:4] explore_dir[4:6]
@@ -175,14 +176,21 @@ int swarm_critic_state(const SwarmParams* params, const SwarmState* state, float
 
 /* `steps` consecutive env.step calls with device-resident actions (steps,E,N[,2]); only the
  * last observation is kept, rewards are accumulated into out->reward, time_out is OR-ed.
- * actions_stride_steps = elements between consecutive steps (0 repeats one action). */
+ * actions_stride_steps = elements between consecutive steps (0 repeats one action: the trainers'
+ * decision-period loop).  Wheel-action variants run as ONE fused launch per <= 32 steps (state in
+ * registers between steps, sensors only after the last one); module-action variants as `steps`
+ * back-to-back launches.  Either way the results equal `steps` swarm_step calls bit for bit.
+ * Injected noise tensors are rejected (single-step only). */
 int swarm_rollout(const SwarmParams* params, const SwarmState* state, const void* actions,
                   int64_t actions_stride_steps, const SwarmNoise* noise, const SwarmOut* out,
                   int E, int steps, void* stream);
 
-/* Host-buffer convenience path (what a non-torch caller binds): copies the action batch
- * host->device, runs one step, copies obs/reward/time_out back, synchronises `stream`.
- * `state` holds DEVICE pointers; actions/obs/reward/time_out are HOST pointers. */
+/* Host-buffer path (what a non-torch caller binds): copies the action batch host->device, runs
+ * one step, copies obs/reward/time_out back, synchronises `stream`.  Batches of >= 4096 envs are
+ * processed as up to 8 env chunks whose observation downloads run on a library-owned copy stream,
+ * overlapping the next chunk's upload + step (use pinned host memory).  `state` holds DEVICE
+ * pointers; actions/obs/reward/time_out are HOST pointers; dev_actions is a device staging buffer
+ * of the action batch's size. */
 int swarm_host_step(const SwarmParams* params, const SwarmState* state, const void* actions_host,
                     const SwarmNoise* noise, float* obs_host, float* reward_host,
                     uint8_t* time_out_host, void* dev_actions, const SwarmOut* dev_out, int E,
