@@ -375,6 +375,23 @@ def main():
                                                  "path": "swarm_rollout, fused kernel" if not r["discrete"] else
                                                          "swarm_rollout, 5 launches"}
 
+        # BASELINE.json configs[0]: the manual_control.py kinematic path, 1 env x 20 robots, one 180 s episode
+        # (1800 ticks of MC:721-757), wall clock through StandaloneSwarmEnv.tick (launch-latency bound at E = 1)
+        from swarmacb_isaaclab_b200.standalone import StandaloneSwarmEnv
+        mc = StandaloneSwarmEnv(20, device, "SwarmACB-XOR-v0", num_envs=1, seed=0)
+        ids = torch.randint(0, 6, (64, 1, N), device=device)
+        for w in range(20):
+            mc.tick(ids[w % 64])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(1800):
+            mc.tick(ids[k % 64])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        others["manual_control_xor_1env"] = {"value": N * 1800 / dt, "unit": "agent-steps/s (1 GPU, wall clock)",
+                                             "ms_per_step": dt / 1800 * 1e3,
+                                             "config": "BASELINE.json configs[0]: 1 env x 20 e-pucks, 1800-tick rollout"}
+
     cpu = None if args.no_cpu else cpu_baseline(mission, head["mode"])
 
     line = {

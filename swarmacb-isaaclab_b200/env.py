@@ -295,6 +295,38 @@ class SwarmEnv:
     def close(self):
         pass
 
+    # ── checkpoint / resume (the reference never saves env state) ───────────
+    _STATE_TENSORS = {
+        "pos": "agent_pos", "yaw": "agent_yaw", "prev_ground": "prev_ground_color", "cached_left": "_cached_left_vel",
+        "cached_right": "_cached_right_vel", "fsm": "_fsm", "beh_cache": "_beh_cache", "mission_flags": "_mission_flags",
+        "episode_length_buf": "episode_length_buf", "episode_group_reward": "_episode_group_reward",
+        "completed_group_reward": "completed_group_reward",
+        "completed_terminal_critic_state": "completed_terminal_critic_state", "obs": "_obs",
+    }
+
+    def state_dict(self) -> dict:
+        """Everything needed to resume a run bit for bit: the SwarmState arrays, the last observation and the Philox
+        position (seed, step counter, env offset).  Tensors are detached CPU copies (``torch.save``-able)."""
+        sd = {k: getattr(self, attr).detach().cpu().clone() for k, attr in self._STATE_TENSORS.items()}
+        sd["meta"] = {"seed": self._seed, "step_counter": self._step_counter, "env_offset": self._env_offset,
+                      "num_envs": self.num_envs, "mission": int(self.params.mission), "obs_dim": self.obs_dim,
+                      "discrete_actions": bool(self.params.discrete_actions)}
+        return sd
+
+    def load_state_dict(self, sd: dict):
+        meta = sd["meta"]
+        mine = (self.num_envs, int(self.params.mission), self.obs_dim, bool(self.params.discrete_actions))
+        theirs = (meta["num_envs"], meta["mission"], meta["obs_dim"], meta["discrete_actions"])
+        if mine != theirs:
+            raise ValueError(f"checkpoint is for (envs, mission, obs_dim, discrete) = {theirs}, this env is {mine}")
+        for k, attr in self._STATE_TENSORS.items():
+            dst = getattr(self, attr)
+            dst.copy_(sd[k].to(dst.dtype).reshape(dst.shape))
+        self._seed, self._step_counter = int(meta["seed"]), int(meta["step_counter"])
+        self._env_offset = int(meta["env_offset"])
+        self._injected = {}
+        self._sync_flags()
+
     # ── teacher-forcing helpers for the parity tests ────────────────────────────────────────
     def load_state(self, state: dict):
         """Overwrite the device state from host arrays in the include/swarm_abi.h layouts."""

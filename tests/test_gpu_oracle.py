@@ -352,3 +352,63 @@ def test_headless_runner_random_policy(tmp_path, capsys):
     out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert out["envs"] == 256 and out["env_steps"] == 60 and out["obs_dim"] == 24 and not out["discrete_actions"]
     assert out["episodes_finished"] == 256 * 2 and out["agent_steps_per_s"] > 0
+
+
+@pytest.mark.parametrize("mission,mode", [("for", "daisy"), ("shl", "oc2")])
+def test_checkpoint_resume_is_bit_exact(mission, mode, tmp_path):
+    """state_dict() -> torch.save -> a fresh env's load_state_dict(): the resumed run continues bit for bit
+    (poses, FSM state, counters, Philox position), across a roll-over."""
+    E = 300
+    a = _mk(mission, mode, E)
+    a.reset(seed=4)
+    a.episode_length_buf[::3] = a.max_episode_length - 6
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    discrete = bool(a.params.discrete_actions)
+    acts = (torch.randint(0, 6, (12, E, N, 1), generator=g, device="cuda:0") if discrete
+            else torch.rand(12, E, N, 2, generator=g, device="cuda:0") * 2 - 1)
+    for t in range(4):
+        a.step_tensor(acts[t])
+    torch.save(a.state_dict(), tmp_path / "env.pt")
+    b = _mk(mission, mode, E)
+    b.load_state_dict(torch.load(tmp_path / "env.pt"))
+    assert torch.equal(a._obs, b._obs)
+    rolled = 0
+    for t in range(4, 12):
+        oa, ra, da = a.step_tensor(acts[t])
+        ob, rb, db = b.step_tensor(acts[t])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"t={t}"
+        rolled += int(da.sum())
+    assert rolled == len(range(0, E, 3))
+    sa, sb = a.dump_state(), b.dump_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    with pytest.raises(ValueError):
+        _mk(mission, mode, E + 1).load_state_dict(a.state_dict())
+
+
+def test_philox_packet_loss_statistics():
+    """Production noise: every ordered in-range pair keeps its packet with P = 0.15 (SENS:419-421), independently.
+    Homing has no internal walls and robots never touch the arena faces, so line of sight never blocks and the
+    neighbour count n_i = popcount(kept & in_range) can be read back from ztilde = 1 - 2 / (1 + e^n)."""
+    E = 4096
+    env = _mk("hom", "lily", E)
+    env.reset(seed=7)
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    lut = torch.tensor(list(env.params.ztilde_lut), device="cuda:0")
+    kept = in_range = 0
+    var_num = var_den = 0.0
+    for t in range(12):
+        obs, _, _ = env.step_tensor(torch.randint(0, 6, (E, N, 1), generator=g, device="cuda:0"))
+        n = (obs[..., 3].unsqueeze(-1) - lut).abs().argmin(-1)                       # (E,N) kept neighbour count
+        pos = env.agent_pos
+        d = (pos.unsqueeze(2) - pos.unsqueeze(1)).pow(2).sum(-1).add(1e-8).sqrt()
+        m = ((d < 0.6) & ~torch.eye(N, dtype=torch.bool, device="cuda:0")).sum(-1)  # (E,N) neighbours in range
+        kept += int(n.sum())
+        in_range += int(m.sum())
+        # binomial dispersion: sum (n - m p)^2 ~ sum m p (1 - p)
+        var_num += float(((n - 0.15 * m).double() ** 2).sum())
+        var_den += float((m * 0.15 * 0.85).double().sum())
+    rate = kept / in_range
+    sigma = (0.15 * 0.85 / in_range) ** 0.5
+    assert in_range > 2_000_000 and abs(rate - 0.15) < 5 * sigma + 1e-4, (rate, sigma)
+    assert abs(var_num / var_den - 1.0) < 0.02, var_num / var_den                  # no over/under-dispersion
