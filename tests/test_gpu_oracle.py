@@ -412,3 +412,38 @@ def test_philox_packet_loss_statistics():
     sigma = (0.15 * 0.85 / in_range) ** 0.5
     assert in_range > 2_000_000 and abs(rate - 0.15) < 5 * sigma + 1e-4, (rate, sigma)
     assert abs(var_num / var_den - 1.0) < 0.02, var_num / var_den                  # no over/under-dispersion
+
+
+@pytest.mark.parametrize("mission,mode,E", [("hom", "lily", 4096), ("for", "daisy", 16384), ("dgt", "dandelion", 8192),
+                                            ("shl", "oc2", 16384)])
+def test_baseline_size_batches_equal_oracle(mission, mode, E):
+    """BASELINE.json configs[1..4] at their full per-GPU batch sizes: reset + 3 free-running steps (one with a
+    partial roll-over) against the oracle on the same injected noise - everything bit for bit."""
+    rng = np.random.default_rng(E + len(mission))
+    env = _mk(mission, mode, E)
+    p = env.params
+    oracle.set_threads()
+    host = oracle.new_state(E)
+    noise = dict(rab_u=rng.random((E, N, N), dtype=np.float32), spawn_u=rng.random((6, E, N, 2), dtype=np.float32),
+                 yaw_u=rng.random((E, N), dtype=np.float32))
+    env.inject_noise(**noise)
+    env.reset()
+    obs_o = oracle.reset(p, host, **noise)
+    assert np.array_equal(env._obs.cpu().numpy(), obs_o)
+    env.episode_length_buf[::9] = p.max_episode_length - 2
+    host["episode_length_buf"][::9] = p.max_episode_length - 2
+    for t in range(3):
+        act = rng.integers(0, 6, (E, N), dtype=np.int64) if p.discrete_actions else \
+            (rng.random((E, N, 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+        noise = dict(rab_u=rng.random((E, N, N), dtype=np.float32), turn_dur=rng.integers(1, 5, (E, N, 3)).astype(np.int32),
+                     spawn_u=rng.random((6, E, N, 2), dtype=np.float32), yaw_u=rng.random((E, N), dtype=np.float32))
+        env.inject_noise(**noise)
+        obs, rew, to = env.step_tensor(torch.as_tensor(act, device="cuda:0"))
+        obs_o, rew_o, to_o = oracle.step(p, host, act, **noise)
+        dev = env.dump_state()
+        for k in ("pos", "yaw", "fsm", "prev_ground", "mission_flags", "episode_length_buf", "episode_group_reward",
+                  "completed_group_reward", "cached_left", "cached_right"):
+            assert np.array_equal(dev[k], host[k]), f"{mission}/{mode} E={E} t={t}: {k}"
+        assert np.array_equal(obs.cpu().numpy(), obs_o) and np.array_equal(rew.cpu().numpy(), rew_o)
+        assert np.array_equal(to.cpu().numpy(), to_o)
+    assert host["completed_terminal_critic_state"].any()
