@@ -18,7 +18,7 @@ def main():
     sizes = [int(a) for a in sys.argv[2:]]
     mission, mode, _, task, _ = bench.WORKLOADS[name]
     dev = "cuda:0"
-    flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=dev)
+    flush = None if os.environ.get("SWEEP_WARM_L2") else torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=dev)
     for E in sizes:
         env = SwarmEnv(bench.make_cfg(mission, mode, E, dev))
         env.reset(seed=0)
