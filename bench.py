@@ -374,6 +374,16 @@ def main():
                                                  "ms_per_decision": m5,
                                                  "path": "swarm_rollout, fused kernel" if not r["discrete"] else
                                                          "swarm_rollout, 5 launches"}
+            if name == "sheltering_oc2_16384":
+                # BASELINE.json configs[4] without its trainer (the reference's PyTorch code, not shipped here): the
+                # env side of the OC2 loop at the trainer's cadence - per decision a fresh on-device action sample,
+                # get_critic_state() and one rollout of 5 motion updates - wall clock through the Python API
+                from swarmacb_isaaclab_b200 import runner
+                rr = runner.random_policy_rollout(r["env"], decisions=min(K, 100), decision_period=5, seed=5)
+                others[name]["trainer_cadence_wall_clock"] = {
+                    "value": rr["agent_steps_per_s"], "unit": "agent-steps/s (1 GPU)",
+                    "agent_decisions_per_s": rr["agent_decisions_per_s"], "decisions": rr["decisions"],
+                    "path": "runner.random_policy_rollout: torch action sample + get_critic_state + SwarmEnv.rollout(5)"}
 
         # BASELINE.json configs[0]: the manual_control.py kinematic path, 1 env x 20 robots, one 180 s episode
         # (1800 ticks of MC:721-757), wall clock through StandaloneSwarmEnv.tick (launch-latency bound at E = 1)
