@@ -117,6 +117,36 @@ class SwarmEnv:
     def unwrapped(self):
         return self
 
+    def _spaces(self):
+        """Per-agent spaces the way isaaclab's DirectMARLEnv derives them from the cfg's integer sizes (gymnasium
+        objects when gymnasium is installed, the cfg's integers otherwise)."""
+        obs, act = dict(self.cfg.observation_spaces), dict(self.cfg.action_spaces)
+        try:
+            import gymnasium as gym
+            import numpy as np
+        except ImportError:
+            return obs, act
+        obs = {a: gym.spaces.Box(-np.inf, np.inf, (int(n),), np.float32) for a, n in obs.items()}
+        if self.params.discrete_actions:
+            act = {a: gym.spaces.Discrete(int(self.cfg.num_actions)) for a in act}
+        else:
+            act = {a: gym.spaces.Box(-1.0, 1.0, (int(n),), np.float32) for a, n in act.items()}
+        return obs, act
+
+    @property
+    def observation_spaces(self):
+        return self._spaces()[0]
+
+    @property
+    def action_spaces(self):
+        return self._spaces()[1]
+
+    def observation_space(self, agent):
+        return self.observation_spaces[agent]
+
+    def action_space(self, agent):
+        return self.action_spaces[agent]
+
     @property
     def _has_food(self):  # FOR:36
         return (self._mission_flags & 1).bool()
