@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from .cfg import TASK_CFGS, DirectionalGateEnvCfg
-from .params import N, SwarmNoise, SwarmOut, SwarmState, build_params, pack_fsm, unpack_fsm
+from .params import FSM_STATE_MASK, N, SwarmNoise, SwarmOut, SwarmState, build_params, pack_fsm, unpack_fsm
 
 _AGENTS = [f"epuck_{i}" for i in range(N)]
 
@@ -381,7 +381,9 @@ class SwarmEnv:
             "completed_group_reward": self.completed_group_reward,
             "completed_terminal_critic_state": self.completed_terminal_critic_state,
         }
-        return {k: v.detach().cpu().numpy().copy() for k, v in m.items()}
+        out = {k: v.detach().cpu().numpy().copy() for k, v in m.items()}
+        out["fsm"] &= FSM_STATE_MASK   # bits 18..23 hold pre-drawn turn-duration bits, not reference state
+        return out
 
 
 # ── registry (missions/*/__init__.py of the reference) ─────────────────────────────────────────

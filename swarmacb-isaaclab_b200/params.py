@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 ABI_VERSION = 1
+FSM_STATE_MASK = (1 << 18) - 1   # fsm word: bits 0..17 reference state, 18..23 pre-drawn turn-duration bits
 N = 20
 MAX_SEG = 16
 MAX_INTERNAL = 4

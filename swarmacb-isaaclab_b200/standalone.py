@@ -15,7 +15,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .params import N, SwarmNoise, SwarmOut, SwarmState, build_mc_params, unpack_fsm
+from .params import FSM_STATE_MASK, N, SwarmNoise, SwarmOut, SwarmState, build_mc_params, unpack_fsm
 
 MC_PRE, MC_PHYSICS, MC_POST = 1, 2, 4
 
@@ -142,4 +142,6 @@ class StandaloneSwarmEnv:
         m = {"pos": self.pos, "yaw": self.yaw, "prev_ground": self.prev_ground_color, "fsm": self._fsm,
              "mission_flags": self._mission_flags, "episode_length_buf": self.step_count,
              "episode_group_reward": self.episode_reward}
-        return {k: v.detach().cpu().numpy().copy() for k, v in m.items()}
+        out = {k: v.detach().cpu().numpy().copy() for k, v in m.items()}
+        out["fsm"] &= FSM_STATE_MASK   # bits 18..23 hold pre-drawn turn-duration bits, not reference state
+        return out
