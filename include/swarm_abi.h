@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 1
+#define SWARM_ABI_VERSION 2
 #define SWARM_N 20            /* robots per environment (CFG:39,85) */
 #define SWARM_MAX_SEG 16      /* 12 arena faces + <=4 internal walls */
 #define SWARM_MAX_INTERNAL 4
@@ -131,7 +131,10 @@ typedef struct SwarmState {
 /* fsm word layout (bits): explore_state[0] explore_steps[1:4] explore_dir[4:6]
  *                         photo_avoiding[6] photo_steps[7:10] photo_dir[10:12]
  *                         anti_avoiding[12] anti_steps[13:16] anti_dir[16:18];
- * dir encoding 0 -> 0.0, 1 -> +1.0, 2 -> -1.0 */
+ * dir encoding 0 -> 0.0, 1 -> +1.0, 2 -> -1.0.
+ * Bits 18..23 are not reference state: three 2-bit random numbers the sensor pass of the previous step drew with
+ * its packet-loss Philox blocks; the next dispatch takes the duration of a triggered turn (BEH:302, BEH:386) from
+ * them (1 + two bits, slot = module 1 / 4 / 5) unless SwarmNoise.turn_dur injects the draw (ABI v2). */
 
 /* Injected noise (parity mode).  Any NULL member falls back to the counter-based Philox
  * stream keyed by (seed, global env index, step counter). */
@@ -152,6 +155,9 @@ typedef struct SwarmOut {
   float* obs;       /* (E,N,obs_dim) */
   float* reward;    /* (E)  team reward, same for all 20 agents */
   uint8_t* time_out; /* (E) truncated flag */
+  float* critic;    /* (E,N,5) or NULL: get_critic_state() of the state the call leaves behind (ENV:1279-1290 ->
+                       SENS:545-586), written by the step kernel's epilogue while the pose is still in registers
+                       (ABI v2; swarm_rollout writes it after the last step only) */
 } SwarmOut;
 
 /* One env.step for E environments.  `actions`: int64 (E,N) module ids when
@@ -170,7 +176,8 @@ int swarm_reset(const SwarmParams* params, const SwarmState* state, const SwarmN
 int swarm_sync_episode_flags(const SwarmParams* params, const SwarmState* state, uint64_t next_step_counter,
                              int E, void* stream);
 
-/* get_critic_state(): (E,N,5) = (rho, cos a, sin a, cos b, sin b). */
+/* get_critic_state(): (E,N,5) = (rho, cos a, sin a, cos b, sin b) as its own launch (SwarmOut.critic is the fused
+ * alternative). */
 int swarm_critic_state(const SwarmParams* params, const SwarmState* state, float* critic_out,
                        int E, void* stream);
 

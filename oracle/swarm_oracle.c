@@ -736,6 +736,7 @@ int swarm_oracle_step(const SwarmParams* p, const SwarmState* st, const void* ac
       if (out->time_out[e]) finish_reset(p, st, e, &s);
     }
     observe_env(p, st, nz, out, e, &s);
+    if (out->critic) critic_state(p, &s, out->critic + (size_t)e * N * 5); /* ABI v2: ENV:1279-1290 of the new state */
   }
   return 0;
 }
@@ -756,6 +757,7 @@ int swarm_oracle_reset(const SwarmParams* p, const SwarmState* st, const SwarmNo
     store_pose(st, e, &s);
     finish_reset(p, st, e, &s);
     observe_env(p, st, nz, out, e, &s);
+    if (out->critic) critic_state(p, &s, out->critic + (size_t)e * N * 5);
   }
   return 0;
 }

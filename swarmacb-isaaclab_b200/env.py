@@ -35,8 +35,10 @@ class SwarmEnv:
 
     metadata = {"render_modes": [None]}
 
+    CRITIC_POOL = 4   # buffers get_critic_state() hands out in turn when the critic state is fused into the step
+
     def __init__(self, cfg: DirectionalGateEnvCfg | None = None, render_mode: str | None = None,
-                 env_offset: int = 0, **kwargs):
+                 env_offset: int = 0, fused_critic: bool = True, **kwargs):
         if cfg is None:
             cfg = DirectionalGateEnvCfg()
         self.cfg = cfg
@@ -55,15 +57,15 @@ class SwarmEnv:
 
         E, dev = self.num_envs, self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        self.agent_pos = torch.zeros(E, N, 2, **f32)
-        self.agent_yaw = torch.zeros(E, N, **f32)
+        self._agent_pos = torch.zeros(E, N, 2, **f32)
+        self._agent_yaw = torch.zeros(E, N, **f32)
         self.prev_ground_color = torch.full((E, N), 0.5, **f32)
         self._cached_left_vel = torch.zeros(E, N, **f32)
         self._cached_right_vel = torch.zeros(E, N, **f32)
         self._fsm = torch.zeros(E, N, dtype=torch.int32, device=dev)
         self._beh_cache = torch.zeros(E, 6, N, **f32)
         self._mission_flags = torch.zeros(E, N, dtype=torch.uint8, device=dev)
-        self.episode_length_buf = torch.zeros(E, dtype=torch.long, device=dev)
+        self._episode_length_buf = torch.zeros(E, dtype=torch.long, device=dev)
         self._episode_group_reward = torch.zeros(E, **f32)
         self.completed_group_reward = torch.zeros(E, **f32)
         self.completed_terminal_critic_state = torch.zeros(E, N, 5, **f32)
@@ -75,7 +77,13 @@ class SwarmEnv:
         self._obs = torch.zeros(E, N, self.obs_dim, **f32)
         self._reward = torch.zeros(E, **f32)
         self._time_out = torch.zeros(E, dtype=torch.uint8, device=dev)
-        self._critic = torch.zeros(E, N, 5, **f32)
+        # get_critic_state() fused into the step: see get_critic_state()
+        self.fused_critic = bool(fused_critic)
+        self._critic_pool = [torch.zeros(E, N, 5, **f32) for _ in range(self.CRITIC_POOL)] if fused_critic else []
+        self._critic_slot = 0          # pool buffer the next fused write goes to
+        self._critic_fresh = False     # that buffer holds get_critic_state() of the CURRENT state
+        self._critic_period = 0        # learned number of env.steps between two get_critic_state() calls
+        self._steps_since_critic = 0
         self._terminated = torch.zeros(E, dtype=torch.bool, device=dev)
         self._act_buf = torch.zeros(E, N, self.act_dim, dtype=torch.long if self.params.discrete_actions else torch.float32,
                                     device=dev)
@@ -86,13 +94,41 @@ class SwarmEnv:
             self._beh_cache.data_ptr(), self._mission_flags.data_ptr(), self.episode_length_buf.data_ptr(),
             self._episode_group_reward.data_ptr(), self.completed_group_reward.data_ptr(),
             self.completed_terminal_critic_state.data_ptr(), self._scratch.data_ptr())
-        self._out = SwarmOut(self._obs.data_ptr(), self._reward.data_ptr(), self._time_out.data_ptr())
+        self._out = SwarmOut(self._obs.data_ptr(), self._reward.data_ptr(), self._time_out.data_ptr(), None)
+        self._out_c = SwarmOut(self._obs.data_ptr(), self._reward.data_ptr(), self._time_out.data_ptr(), None)
         self._seed = int(cfg.seed) if getattr(cfg, "seed", None) is not None else 0
         self._step_counter = 0
         self._env_offset = int(env_offset)
         self._injected: dict = {}
         self._obs_views = {a: self._obs[:, i] for i, a in enumerate(self.possible_agents)}
         self._len_version = self.episode_length_buf._version
+        self._pose_version = (self._agent_pos._version, self._agent_yaw._version)
+
+    # The kernels hold raw pointers to these tensors: rebinding the attribute (``env.episode_length_buf = t``) must
+    # not detach the caller's tensor from them, so assignment copies INTO the tensor the kernel sees.
+    @property
+    def episode_length_buf(self) -> torch.Tensor:
+        return self._episode_length_buf
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):
+        self._episode_length_buf.copy_(torch.as_tensor(value, device=self.device))
+
+    @property
+    def agent_pos(self) -> torch.Tensor:
+        return self._agent_pos
+
+    @agent_pos.setter
+    def agent_pos(self, value):
+        self._agent_pos.copy_(torch.as_tensor(value, device=self.device))
+
+    @property
+    def agent_yaw(self) -> torch.Tensor:
+        return self._agent_yaw
+
+    @agent_yaw.setter
+    def agent_yaw(self, value):
+        self._agent_yaw.copy_(torch.as_tensor(value, device=self.device))
 
     # ── device / library binding ────────────────────────────────────────────────────────────
     def _resolve_device(self, name) -> torch.device:
@@ -218,8 +254,8 @@ class SwarmEnv:
             self._seed = int(seed)
         nz = self._noise()
         with self._device_guard():
-            rc = self._lib.swarm_reset(C.byref(self.params), C.byref(self._state), C.byref(nz), C.byref(self._out),
-                                       self.num_envs, self._stream())
+            rc = self._lib.swarm_reset(C.byref(self.params), C.byref(self._state), C.byref(nz),
+                                       C.byref(self._critic_out(self.fused_critic)), self.num_envs, self._stream())
         _lib.check(rc, "swarm_reset")
         return dict(self._obs_views), self.extras
 
@@ -252,10 +288,13 @@ class SwarmEnv:
         act = self._gather_actions(actions)
         self._check_len_buf()
         nz = self._noise()
+        # the critic state rides on the step that the learned cadence says precedes the next get_critic_state()
+        want = self.fused_critic and self._steps_since_critic + 1 == self._critic_period
         with self._device_guard():
             rc = self._lib.swarm_step(C.byref(self.params), C.byref(self._state), C.c_void_p(act.data_ptr()),
-                                      C.byref(nz), C.byref(self._out), self.num_envs, self._stream())
+                                      C.byref(nz), C.byref(self._critic_out(want)), self.num_envs, self._stream())
         _lib.check(rc, "swarm_step")
+        self._steps_since_critic += 1
         return self._obs, self._reward, self._time_out.view(torch.bool)
 
     def step(self, actions: dict):
@@ -267,27 +306,38 @@ class SwarmEnv:
         return dict(self._obs_views), reward_dict, terminated, truncated, self.extras
 
     def rollout(self, actions: torch.Tensor, steps: int | None = None):
-        """``steps`` consecutive env.steps with device-resident actions (T,E,N,act) (or one (E,N,act)
-        action repeated, the trainers' decision_period loop).  Returns (last obs, summed reward, OR-ed time_out)."""
+        """``steps`` consecutive env.steps with device-resident actions.  ``actions`` is either one action per step,
+        shape (T,E,N,act) (then ``steps`` must be None or T), or ONE action (E,N,act) / (E,N) that is repeated
+        ``steps`` times (the trainers' decision_period loop; ``steps`` is required).  Returns (last obs, summed
+        reward, OR-ed time_out).  Raises ValueError on any other shape: the kernel cannot bounds-check the buffer."""
         want = torch.long if self.params.discrete_actions else torch.float32
         E, A = self.num_envs, self.act_dim
+        shape = tuple(actions.shape)
+        if shape == (E, N, A) or (A == 1 and shape == (E, N)):
+            if steps is None:
+                raise ValueError("rollout: `steps` is required when one action is repeated")
+            T, stride = int(steps), 0
+        elif (len(shape) == 4 and shape[1:] == (E, N, A)) or (A == 1 and len(shape) == 3 and shape[1:] == (E, N)):
+            T, stride = int(shape[0]), E * N * A
+            if steps is not None and int(steps) != T:
+                raise ValueError(f"rollout: steps={steps} does not match the {T} per-step actions given")
+        else:
+            raise ValueError(f"rollout: actions must be ({E}, {N}, {A}) (one action, repeated `steps` times) or "
+                             f"(T, {E}, {N}, {A}) (one per step), got {shape}")
+        if T <= 0:
+            raise ValueError("rollout: steps must be > 0")
         if actions.dtype != want or actions.device != self.device:
             actions = actions.to(device=self.device, dtype=want)
         actions = actions.contiguous()
-        if actions.dim() == 4 or (actions.dim() == 3 and actions.shape[0] != E):
-            T = actions.shape[0]
-            stride = E * N * A
-        else:
-            T, stride = int(steps), 0
-        if steps is not None:
-            T = int(steps)
         self._check_len_buf()
         nz = self._noise()
         self._step_counter += T - 1
         with self._device_guard():
             rc = self._lib.swarm_rollout(C.byref(self.params), C.byref(self._state), C.c_void_p(actions.data_ptr()),
-                                         stride, C.byref(nz), C.byref(self._out), E, T, self._stream())
+                                         stride, C.byref(nz), C.byref(self._critic_out(self.fused_critic)), E, T,
+                                         self._stream())
         _lib.check(rc, "swarm_rollout")
+        self._steps_since_critic += T
         return self._obs, self._reward, self._time_out.view(torch.bool)
 
     def step_host(self, actions_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
@@ -309,13 +359,43 @@ class SwarmEnv:
             rc = self._lib.swarm_host_step(C.byref(self.params), C.byref(self._state), C.c_void_p(actions_host.data_ptr()),
                                            C.byref(nz), C.c_void_p(obs_host.data_ptr()), C.c_void_p(reward_host.data_ptr()),
                                            C.c_void_p(time_out_host.data_ptr()), C.c_void_p(self._act_buf.data_ptr()),
-                                           C.byref(self._out), E, self._stream())
+                                           C.byref(self._critic_out(False)), E, self._stream())
         _lib.check(rc, "swarm_host_step")
+        self._steps_since_critic += 1
         return obs_host, reward_host, time_out_host
 
+    def _critic_out(self, want: bool) -> SwarmOut:
+        """The SwarmOut block of the next call: with ``want`` the kernel also writes get_critic_state() of the state
+        it leaves behind into the current pool buffer."""
+        self._critic_fresh = bool(want)
+        if not want:
+            return self._out
+        self._out_c.critic = self._critic_pool[self._critic_slot].data_ptr()
+        self._pose_version = (self._agent_pos._version, self._agent_yaw._version)
+        return self._out_c
+
     def get_critic_state(self) -> torch.Tensor:
-        """(E,N,5) = (rho, cos alpha, sin alpha, cos beta, sin beta), ENV:1279-1290."""
-        out = torch.empty(self.num_envs, N, 5, dtype=torch.float32, device=self.device)
+        """(E,N,5) = (rho, cos alpha, sin alpha, cos beta, sin beta), ENV:1279-1290.
+
+        With ``fused_critic`` (default) the step kernel computes it in its epilogue, while the pose is still in
+        registers: reset() and rollout() always do, step() does on the step that - by the cadence observed so far
+        (the trainers ask once per decision, every ``decision_period`` steps) - precedes the next call.  This call
+        then launches nothing and returns one of CRITIC_POOL rotating buffers: the tensor stays untouched until
+        CRITIC_POOL - 1 further get_critic_state() calls (the reference's trainers copy it into their rollout buffer
+        within the same decision).  When the prediction missed, or agent_pos / agent_yaw were written from outside
+        since, it falls back to the stand-alone kernel.  ``fused_critic=False`` returns a fresh tensor per call."""
+        if not self.fused_critic:
+            out = torch.empty(self.num_envs, N, 5, dtype=torch.float32, device=self.device)
+        else:
+            out = self._critic_pool[self._critic_slot]
+            self._critic_slot = (self._critic_slot + 1) % self.CRITIC_POOL
+            if self._steps_since_critic > 0:
+                self._critic_period = self._steps_since_critic
+            self._steps_since_critic = 0
+            fresh = self._critic_fresh and self._pose_version == (self._agent_pos._version, self._agent_yaw._version)
+            self._critic_fresh = False
+            if fresh:
+                return out
         with self._device_guard():
             rc = self._lib.swarm_critic_state(C.byref(self.params), C.byref(self._state), C.c_void_p(out.data_ptr()),
                                               self.num_envs, self._stream())
@@ -355,6 +435,7 @@ class SwarmEnv:
         self._seed, self._step_counter = int(meta["seed"]), int(meta["step_counter"])
         self._env_offset = int(meta["env_offset"])
         self._injected = {}
+        self._critic_fresh = False
         self._sync_flags()
 
     # ── teacher-forcing helpers for the parity tests ────────────────────────────────────────
@@ -370,6 +451,7 @@ class SwarmEnv:
         }
         for k, dst in m.items():
             dst.copy_(torch.as_tensor(state[k]).to(dst.dtype).reshape(dst.shape))
+        self._critic_fresh = False
         self._sync_flags()
 
     def dump_state(self) -> dict:

@@ -14,7 +14,7 @@ import math
 import numpy as np
 import torch
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FSM_STATE_MASK = (1 << 18) - 1   # fsm word: bits 0..17 reference state, 18..23 pre-drawn turn-duration bits
 N = 20
 MAX_SEG = 16
@@ -74,7 +74,7 @@ class SwarmNoise(C.Structure):
 
 
 class SwarmOut(C.Structure):
-    _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("time_out", C.c_void_p)]
+    _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("time_out", C.c_void_p), ("critic", C.c_void_p)]
 
 
 # E-puck IR sensor bearings, SENS:28-37, and RAB projection axes, SENS:40-41.

@@ -1,5 +1,7 @@
 """GPU parity at scale: CUDA step vs the CPU oracle on seeded random rollouts (teacher-forced per step),
 plus size-independent properties at BASELINE.json's full sizes."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -43,7 +45,7 @@ def _cluster(rng, E, frac=0.5):
 @pytest.mark.parametrize("mission,mode,dec", CASES)
 def test_cuda_vs_oracle_rollout(mission, mode, dec):
     E, T = 384, 12
-    rng = np.random.default_rng(hash((mission, mode)) % 2**31)
+    rng = np.random.default_rng(zlib.crc32(f"{mission}/{mode}".encode()))  # stable across processes (str hash is salted)
     env = _mk(mission, mode, E, dec)
     p = env.params
     host = oracle.new_state(E)

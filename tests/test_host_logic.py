@@ -237,3 +237,45 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0
+
+
+def test_rollout_rejects_ambiguous_or_short_action_buffers():
+    """swarm_rollout cannot bounds-check the action buffer, so SwarmEnv.rollout validates shapes itself
+    (host logic, exercised on CPU tensors with the oracle behind the C-ABI call sites)."""
+    import pytest
+    import fixtures
+    from oracle_env import OracleBackedEnv
+    E = 4
+    for mission, mode, A, dt in (("xor", "cyclamen", 1, torch.long), ("dgt", "dandelion", 2, torch.float32)):
+        env = OracleBackedEnv(fixtures.make_cfg(mission, mode, E))
+        env.reset()
+        one = torch.zeros(E, P.N, A, dtype=dt)
+        per_step = torch.zeros(3, E, P.N, A, dtype=dt)
+        env.rollout(one, 2)                      # one action, repeated
+        env.rollout(per_step)                    # one action per step
+        env.rollout(per_step, 3)
+        with pytest.raises(ValueError):
+            env.rollout(one)                     # repeated action without `steps`
+        with pytest.raises(ValueError):
+            env.rollout(per_step, 5)             # more steps than actions: would read past the buffer
+        with pytest.raises(ValueError):
+            env.rollout(torch.zeros(E, E, P.N, A, dtype=dt)[:, :2], 2)   # wrong env count
+        with pytest.raises(ValueError):
+            env.rollout(one, 0)
+    # (T, E, N) integer ids are accepted for module actions; a first dimension that happens to equal E is still per-step
+    env = OracleBackedEnv(fixtures.make_cfg("xor", "cyclamen", E))
+    env.reset()
+    env.rollout(torch.zeros(E, E, P.N, dtype=torch.long))
+    assert int(env.episode_length_buf[0]) == E
+
+
+def test_state_attribute_assignment_copies_into_the_kernel_tensor():
+    import fixtures
+    from oracle_env import OracleBackedEnv
+    env = OracleBackedEnv(fixtures.make_cfg("hom", "lily", 3))
+    env.reset()
+    ptr = env.episode_length_buf.data_ptr()
+    env.episode_length_buf = torch.tensor([5, 6, 7])
+    assert env.episode_length_buf.data_ptr() == ptr and env.episode_length_buf.tolist() == [5, 6, 7]
+    env.agent_pos = torch.zeros(3, P.N, 2)
+    assert float(env.agent_pos.abs().max()) == 0.0
