@@ -149,6 +149,13 @@ typedef struct SwarmNoise {
   int64_t env_offset;      /* global index of env 0 of this shard (multi-GPU invariance) */
   const float* rab_u2;     /* (E,N,N) second packet-loss draw of a manual-control tick (MC:435) */
   const float* mc_spawn_u; /* (E,N,3) radius, angle, yaw draws of MC:252-258 */
+  /* ENV:1262 re-solves ALL envs of the batch whenever ANY env resets.  By default "the batch" is what this call sees
+   * (its E envs: the kernels keep the flag themselves, see swarm_sync_episode_flags).  A job that shards one batch
+   * over several GPUs and whose episode counters are not in lockstep can hand in the job-wide flag instead
+   * (ABI v2): any_reset_mode = 1 and bit t of any_reset_bits = "some env of the JOB times out at step t of this
+   * call" (bit 0 for swarm_step; swarm_rollout then takes at most 32 steps). */
+  int32_t any_reset_mode;
+  uint32_t any_reset_bits;
 } SwarmNoise;
 
 typedef struct SwarmOut {

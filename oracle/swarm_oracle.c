@@ -725,7 +725,9 @@ int swarm_oracle_step(const SwarmParams* p, const SwarmState* st, const void* ac
     store_pose(st, e, &s);
   }
 
-  /* phase 2: ENV:1262 re-solves ALL envs when any env reset; then observe */
+  /* phase 2: ENV:1262 re-solves ALL envs when any env reset; then observe.  A sharded job may hand in the job-wide
+   * flag (ABI v2, SwarmNoise.any_reset_mode). */
+  if (nz->any_reset_mode == 1) any_reset = (int)(nz->any_reset_bits & 1u);
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < E; ++e) {
     Pose s;

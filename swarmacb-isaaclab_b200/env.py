@@ -100,6 +100,7 @@ class SwarmEnv:
         self._step_counter = 0
         self._env_offset = int(env_offset)
         self._injected: dict = {}
+        self.job_reset_clock = None    # sharding.JobResetClock: job-wide ENV:1262 coupling for de-synchronised shards
         self._obs_views = {a: self._obs[:, i] for i, a in enumerate(self.possible_agents)}
         self._len_version = self.episode_length_buf._version
         self._pose_version = (self._agent_pos._version, self._agent_yaw._version)
@@ -220,7 +221,7 @@ class SwarmEnv:
             inj["yaw_u"] = torch.as_tensor(yaw_u, dtype=torch.float32, device=dev).reshape(E, N).contiguous()
         self._injected = inj
 
-    def _noise(self) -> SwarmNoise:
+    def _noise(self, steps: int = 1) -> SwarmNoise:
         inj, self._injected = self._injected, {}
         self._noise_keepalive = inj
         nz = SwarmNoise()
@@ -231,8 +232,19 @@ class SwarmEnv:
         nz.seed = self._seed
         nz.step_counter = self._step_counter
         nz.env_offset = self._env_offset
+        if self.job_reset_clock is not None and steps > 0:
+            nz.any_reset_mode = 1
+            nz.any_reset_bits = self.job_reset_clock.bits(self._step_counter, steps)
         self._step_counter += 1
         return nz
+
+    def attach_job_reset_clock(self, group=None, peers=None):
+        """Multi-GPU jobs with de-synchronised episode counters: make ENV:1262's "any env reset -> re-solve all envs"
+        job-wide instead of per shard (see sharding.JobResetClock).  Collective: call it on every rank."""
+        from .sharding import JobResetClock
+        self._check_len_buf()
+        self.job_reset_clock = JobResetClock(self, group, peers)
+        return self.job_reset_clock
 
     def _sync_flags(self):
         """Rebuild the kernel's rotating any-reset flags after episode_length_buf was written from outside."""
@@ -241,6 +253,8 @@ class SwarmEnv:
                                                     self.num_envs, self._stream())
         _lib.check(rc, "swarm_sync_episode_flags")
         self._len_version = self.episode_length_buf._version
+        if self.job_reset_clock is not None:
+            self.job_reset_clock.rebuild(self)
 
     def _check_len_buf(self):
         if self.episode_length_buf._version != self._len_version:
@@ -252,11 +266,13 @@ class SwarmEnv:
     def reset(self, seed: int | None = None, options: dict | None = None):
         if seed is not None:
             self._seed = int(seed)
-        nz = self._noise()
+        nz = self._noise(0)
         with self._device_guard():
             rc = self._lib.swarm_reset(C.byref(self.params), C.byref(self._state), C.byref(nz),
                                        C.byref(self._critic_out(self.fused_critic)), self.num_envs, self._stream())
         _lib.check(rc, "swarm_reset")
+        if self.job_reset_clock is not None:
+            self.job_reset_clock.rebuild(self)
         return dict(self._obs_views), self.extras
 
     def _gather_actions(self, actions) -> torch.Tensor:
@@ -330,7 +346,7 @@ class SwarmEnv:
             actions = actions.to(device=self.device, dtype=want)
         actions = actions.contiguous()
         self._check_len_buf()
-        nz = self._noise()
+        nz = self._noise(T)
         self._step_counter += T - 1
         with self._device_guard():
             rc = self._lib.swarm_rollout(C.byref(self.params), C.byref(self._state), C.c_void_p(actions.data_ptr()),

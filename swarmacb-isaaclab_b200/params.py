@@ -70,6 +70,7 @@ class SwarmNoise(C.Structure):
         ("rab_u", C.c_void_p), ("turn_dur", C.c_void_p), ("spawn_u", C.c_void_p), ("yaw_u", C.c_void_p),
         ("spawn_rounds", I), ("seed", C.c_uint64), ("step_counter", C.c_uint64), ("env_offset", C.c_int64),
         ("rab_u2", C.c_void_p), ("mc_spawn_u", C.c_void_p),
+        ("any_reset_mode", I), ("any_reset_bits", C.c_uint32),
     ]
 
 

@@ -4,7 +4,15 @@ Environments are independent, so a job of ``total_envs`` is cut into contiguous 
 rank (one process per GPU).  The step has NO collective; the only exchange is a latency-bound
 all-reduce(sum) of a five-float episode-metric vector at report time (NCCL over NVLink on GPUs, gloo
 in the CPU tests).  The in-kernel Philox stream is keyed by the GLOBAL env index
-(``env_offset + local index``), so a trajectory does not depend on how many GPUs the job uses.
+(``env_offset + local index``), so a trajectory does not depend on how many GPUs the job uses -
+
+with one caveat the reference itself carries: ``_reset_idx`` re-solves the collisions of ALL environments of the
+batch whenever ANY of them times out (ENV:1262).  A shard sees only its own environments, so that coupling is per
+shard by default - exactly what the reference does when a job runs as independent processes of E/G environments.
+While all episode counters move in lockstep (the normal case: every env starts at 0) every shard rolls over at the
+same step and sharded == unsharded bit for bit.  With de-synchronised counters (a resumed checkpoint, counters
+written from outside) attach a :class:`JobResetClock`: one all-reduce of an L-bit phase mask when it is built, no
+collective per step, and every shard is told the job-wide flag (``SwarmNoise.any_reset_mode``).
 """
 from __future__ import annotations
 
@@ -56,3 +64,42 @@ class EpisodeMetrics:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
         return dict(zip(METRIC_NAMES, out.tolist()))
+
+
+class JobResetClock:
+    """Which upcoming steps see a time-out SOMEWHERE in the job (ENV:1262 couples the whole batch).
+
+    Episodes only ever end by time-out (``terminated`` is always False, ENV:1200-1209), so env e rolls over at the
+    steps ``k = (L - 1 - len_e) mod L`` (mod L): the job-wide set of roll-over phases is an L-bit mask.  It is built
+    ONCE - per-rank mask from the rank's counters, OR-ed over the ranks with one all-reduce - and then answers every
+    step from the host without touching the device.  It must be rebuilt (collectively) after episode_length_buf is
+    written from outside or a checkpoint is loaded; ``SwarmEnv`` does that itself when a clock is attached.
+    """
+
+    def __init__(self, env, group=None, peers=None):
+        """``group``: the process group of the job (one shard per rank).  ``peers``: further shards living in THIS
+        process (several envs on one GPU, or one per stream) whose counters belong to the same job."""
+        self.group = group
+        self.peers = list(peers) if peers else []
+        self.rebuild(env)
+
+    def rebuild(self, env):
+        L = int(env.max_episode_length)
+        phase = torch.zeros(L, dtype=torch.int32, device=env.episode_length_buf.device)
+        for shard in [env] + [p for p in self.peers if p is not env]:
+            lens = shard.episode_length_buf.to(torch.long)
+            # env e times out at the step where its counter reads L - 1, i.e. (L - 1 - len_e) steps from now
+            phase[(L - 1 - lens.clamp(0, L - 1)) % L] = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(phase, op=dist.ReduceOp.MAX, group=self.group)
+        self.phase = phase.cpu().numpy().astype(bool)
+        self.period = L
+        self.origin = int(env._step_counter)
+
+    def bits(self, step_counter: int, n_steps: int = 1) -> int:
+        """Bit t set = some env of the job times out at step ``step_counter + t``."""
+        out = 0
+        for t in range(n_steps):
+            if self.phase[(step_counter + t - self.origin) % self.period]:
+                out |= 1 << t
+        return out

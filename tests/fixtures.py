@@ -43,12 +43,17 @@ def make_cfg(mission: str, mode: str, num_envs: int, decimation: int = 1, device
 
 
 class Fixture:
-    def __init__(self, path):
-        z = np.load(path)
-        self.path = path
-        self.name = os.path.basename(path)[:-4]
-        self.meta = json.loads(str(z["meta"]))
-        self.z = {k: z[k] for k in z.files if k != "meta"}
+    def __init__(self, path=None, meta=None, arrays=None):
+        """From a committed .npz, or (``meta``/``arrays``) straight from tests/golden/gen_golden.make_case-style
+        records of the live reference (tests/test_oracle_vs_live_reference.py)."""
+        if path is not None:
+            z = np.load(path)
+            self.path = path
+            self.name = os.path.basename(path)[:-4]
+            self.meta = json.loads(str(z["meta"]))
+            self.z = {k: z[k] for k in z.files if k != "meta"}
+        else:
+            self.path, self.name, self.meta, self.z = None, "live", dict(meta), dict(arrays)
         m = self.meta
         self.E, self.steps = m["E"], m["steps"]
         self.cfg = make_cfg(m["mission"], m["mode"], m["E"], m["decimation"])

@@ -137,13 +137,13 @@ def test_full_size_properties(mission, mode, E):
     assert torch.equal(env2.agent_pos, env.agent_pos) and torch.equal(obs2, obs)
 
 
-def test_sharded_rollout_equals_unsharded():
-    """SURVEY 8e: the Philox stream is keyed by the global env index, so cutting a job into shards
-    (one per GPU) reproduces the unsharded trajectory bit for bit."""
+def _sharded_setup(episode_length_s=None):
     from swarmacb_isaaclab_b200.env import SwarmEnv
     from swarmacb_isaaclab_b200.sharding import shard_cfg
     base = fixtures.make_cfg("for", "daisy", 96, device="cuda:0")
     base.seed = 11
+    if episode_length_s is not None:
+        base.episode_length_s = episode_length_s
     whole = SwarmEnv(base)
     parts = []
     for r in range(3):
@@ -152,14 +152,71 @@ def test_sharded_rollout_equals_unsharded():
     whole.reset()
     for p_ in parts:
         p_.reset()
+    return whole, parts
+
+
+def _sharded_run(whole, parts, steps, expect_equal=True):
     g = torch.Generator(device="cuda:0").manual_seed(5)
-    for t in range(25):
+    rollovers, equal = 0, True
+    for t in range(steps):
         act = torch.randint(0, 6, (96, N, 1), generator=g, device="cuda:0")
-        obs, rew, _ = whole.step_tensor(act)
+        obs, rew, to = whole.step_tensor(act)
         outs = [p_.step_tensor(act[32 * r: 32 * (r + 1)].contiguous()) for r, p_ in enumerate(parts)]
-        assert torch.equal(obs, torch.cat([o[0] for o in outs]))
-        assert torch.equal(rew, torch.cat([o[1] for o in outs]))
-    assert torch.equal(whole.agent_pos, torch.cat([p_.agent_pos for p_ in parts]))
+        rollovers += int(to.sum())
+        # counters, rewards before any divergence and time-out flags never depend on the re-solve coupling
+        assert torch.equal(to, torch.cat([o[2] for o in outs])), t
+        same = torch.equal(obs, torch.cat([o[0] for o in outs])) and torch.equal(rew, torch.cat([o[1] for o in outs]))
+        if expect_equal:
+            assert same, f"step {t}"
+        equal = equal and same
+    same_pos = torch.equal(whole.agent_pos, torch.cat([p_.agent_pos for p_ in parts]))
+    if expect_equal:
+        assert same_pos
+    return rollovers, equal and same_pos
+
+
+def test_sharded_rollout_equals_unsharded():
+    """SURVEY 8e: the Philox stream is keyed by the global env index, so cutting a job into shards
+    (one per GPU) reproduces the unsharded trajectory bit for bit - across synchronised roll-overs too
+    (1 s episodes = 10 steps: every env of every shard respawns and is re-solved at the same steps)."""
+    whole, parts = _sharded_setup()
+    _sharded_run(whole, parts, 25)
+    whole, parts = _sharded_setup(episode_length_s=1.0)
+    rollovers, _ = _sharded_run(whole, parts, 34)
+    assert rollovers == 3 * 96
+
+
+def test_sharded_rollout_with_desynchronised_counters():
+    """ENV:1262 re-solves ALL envs of the batch whenever ANY env times out.  With episode counters out of lockstep the
+    batch-wide flag differs between a shard and the whole job; the JobResetClock hands every shard the job-wide
+    flag (one all-reduce when it is built, none per step) and restores bit-identity.  Crowded spawn (Homing strip)
+    so that the extra re-solve actually moves robots."""
+    from swarmacb_isaaclab_b200.env import SwarmEnv
+    from swarmacb_isaaclab_b200.sharding import shard_cfg
+
+    def setup(with_clock):
+        base = fixtures.make_cfg("hom", "lily", 96, device="cuda:0")
+        base.seed, base.episode_length_s = 4, 2.0          # 20-step episodes
+        whole = SwarmEnv(base)
+        parts = []
+        for r in range(3):
+            c, off = shard_cfg(base, 96, 3, r, device="cuda:0")
+            parts.append(SwarmEnv(c, env_offset=off))
+        for env in [whole] + parts:
+            env.reset()
+        lens = torch.zeros(96, dtype=torch.long)
+        lens[:32] = torch.arange(32) % 20                    # only shard 0 is staggered: it rolls over at every step,
+        whole.episode_length_buf = lens                      # shards 1 and 2 only every 20th
+        for r, p_ in enumerate(parts):
+            p_.episode_length_buf = lens[32 * r: 32 * (r + 1)]
+        if with_clock:
+            for p_ in parts:
+                p_.attach_job_reset_clock(peers=parts)
+        return whole, parts
+
+    rollovers, equal = _sharded_run(*setup(False), 45, expect_equal=False)
+    assert rollovers > 96 and not equal       # per-shard coupling (the default) is visible once counters are staggered
+    _sharded_run(*setup(True), 45)            # job-wide flags: bit-identical again
 
 
 def test_dict_api_and_zero_copy_actions():

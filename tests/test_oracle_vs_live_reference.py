@@ -1,0 +1,159 @@
+"""Reference-scale parity of the CPU oracle against the LIVE reference (build container only; skipped where
+/root/reference is absent).
+
+For every mission x {4-dim discrete (cyclamen), 24-dim discrete (daisy), 24-dim continuous (dandelion)} the unmodified
+reference env classes run free (random actions, staggered episode counters so that time-outs, respawns and the
+all-env re-solve of ENV:1262 happen all along) from a warmed-up mid-episode state; every step is recorded with its
+noise (tests/golden/gen_golden.record_step) and replayed through the oracle teacher-forced.  Asserted: zero mismatches
+of counters / rewards / time-outs / FSM state / ground colours / mission flags, poses within 1e-5 m / 1e-5 rad,
+observations within 1e-4.  Reported ("report, not hide"): how many robot states came within 1e-6 of a zone
+or trigger threshold, i.e. how often a last-ulp difference between the oracle's deterministic sin/cos/atan2 and the
+reference's SLEEF values could have flipped a discrete outcome.
+
+Size: SWARM_PARITY_ROBOT_STEPS robot-steps per case (default 20 000 so the CPU suite stays short; the committed
+report profiles/r02_reference_parity.json comes from a run with 1 000 000).
+"""
+import copy
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import fixtures
+from oracle import oracle
+from swarmacb_isaaclab_b200.params import N
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present")
+
+TARGET = int(os.environ.get("SWARM_PARITY_ROBOT_STEPS", "20000"))
+REPORT = os.environ.get("SWARM_PARITY_REPORT", "")
+EPS = 1e-6
+MISSIONS = ("dgt", "xor", "hom", "for", "shl")
+MODES = ("cyclamen", "daisy", "dandelion")
+
+
+def _circle(pos, cx, cy, r_sq):
+    d = np.hypot(pos[..., 0].astype(np.float64) - cx, pos[..., 1].astype(np.float64) - cy)
+    return np.abs(d - np.sqrt(float(r_sq)))
+
+
+def boundary_margins(p, pos, beh_cache):
+    """Distance (m, or sensor units) of every robot state to each discrete decision boundary of the step."""
+    z = [float(v) for v in p.zone]
+    x, y = pos[..., 0].astype(np.float64), pos[..., 1].astype(np.float64)
+    inf = np.full(x.shape, np.inf)
+    m = {}
+    if p.mission == 0:    # DGT ground colours, ENV:707-750
+        in_gate_y = (y > z[1]) & (y < z[2])
+        m["gate |x|=hw"] = np.where(in_gate_y, np.abs(np.abs(x) - z[0]), inf)
+        m["gate y=south"] = np.where(np.abs(x) < z[0], np.abs(y - z[1]), inf)
+        m["gate/corridor y"] = np.where(np.abs(x) < max(z[0], z[3]), np.abs(y - z[2]), inf)
+        in_corr_y = (y >= z[2]) & (y < z[4])
+        m["corridor |x|=hw"] = np.where(in_corr_y, np.abs(np.abs(x) - z[3]), inf)
+        m["corridor y=north"] = np.where(np.abs(x) < z[3], np.abs(y - z[4]), inf)
+    elif p.mission == 1:  # XOR targets, XOR:117
+        m["target 0 radius"], m["target 1 radius"] = _circle(pos, z[0], z[1], z[4]), _circle(pos, z[2], z[3], z[4])
+    elif p.mission == 2:  # HOM goal, HOM:79
+        m["goal radius"] = _circle(pos, z[0], z[1], z[4])
+    elif p.mission == 3:  # FOR food discs / pickup squares / nest edge, FOR:104-117
+        m["food 0 disc"], m["food 1 disc"] = _circle(pos, z[0], z[1], z[4]), _circle(pos, z[2], z[3], z[4])
+        for k, (cx, cy) in enumerate(((z[0], z[1]), (z[2], z[3]))):
+            ax, ay = np.abs(x - cx), np.abs(y - cy)
+            m[f"food {k} square"] = np.minimum(np.where(ay <= z[5], np.abs(ax - z[5]), inf),
+                                               np.where(ax <= z[5], np.abs(ay - z[5]), inf))
+        m["nest edge"] = np.abs(y - z[6])
+    else:                 # SHL black discs + shelter rectangle, SHL:114-122
+        m["black 0 radius"], m["black 1 radius"] = _circle(pos, z[0], z[1], z[4]), _circle(pos, z[2], z[3], z[4])
+        in_y, in_x = (y >= z[9]) & (y <= z[10]), (x >= z[7]) & (x <= z[8])
+        m["shelter x edges"] = np.where(in_y, np.minimum(np.abs(x - z[7]), np.abs(x - z[8])), inf)
+        m["shelter y edges"] = np.where(in_x, np.minimum(np.abs(y - z[9]), np.abs(y - z[10])), inf)
+    if p.discrete_actions:  # avoidance trigger, BEH:245-251, on the cached sensor scalars the next dispatch reads
+        pv, pa = beh_cache[:, 0].astype(np.float64), beh_cache[:, 1].astype(np.float64)
+        m["prox_value = threshold"] = np.abs(pv - float(p.prox_threshold))
+        m["|prox_angle| = pi/2"] = np.where(pv >= float(p.prox_threshold), np.abs(np.abs(pa) - np.pi / 2), inf)
+    return m
+
+
+def run_case(mission, mode, target):
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import gen_golden
+    import refstub
+    E = 32 if target <= 50000 else 512
+    steps = max(8, -(-target // (E * N)))
+    warm = 10 if target <= 50000 else 40
+    seed = 9000 + 17 * MISSIONS.index(mission) + MODES.index(mode)
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    env = refstub.make_ref_env(mission, mode, E)
+    gen_golden.install_tags(gen_golden.TAP)
+    env.reset()
+    L = int(env.max_episode_length)
+    # staggered counters: a steady trickle of time-outs (and of ENV:1262 all-env re-solves) through the whole run
+    env.episode_length_buf[:] = torch.randint(0, L - warm - 1, (E,), generator=gen)
+    env.episode_length_buf[: max(2, E // 16)] = L - warm - torch.randint(1, steps, (max(2, E // 16),), generator=gen)
+    agents = env.cfg.possible_agents
+    for _ in range(warm):
+        a = gen_golden.random_actions(env, gen)
+        env.step({n: a[:, i] for i, n in enumerate(agents)})
+    stats = {"mission": mission, "mode": mode, "envs": E, "steps": steps, "robot_steps": 0, "resets": 0,
+             "max_pos_err": 0.0, "max_yaw_err": 0.0, "max_obs_err": 0.0, "violations": [], "near_boundary": {}}
+    meta = dict(mission=mission, mode=mode, scenario="live", E=E, N=N, steps=1, seed=seed, decimation=1,
+                discrete=bool(env.cfg.discrete_actions), obs_dim=int(env.cfg.observation_spaces[agents[0]]),
+                max_episode_length=L)
+    for t in range(steps):
+        rec = gen_golden.record_step(env, gen_golden.random_actions(env, gen))
+        arrays = {k: np.asarray(v)[None] for k, v in rec.items()}
+        arrays["rab_keep"] = np.packbits(arrays["rab_keep"].reshape(1, -1), axis=1)
+        fx = fixtures.Fixture(meta=meta, arrays=arrays)
+        case = fx.step_case(0)
+        state = copy.deepcopy(case["pre"])
+        obs, reward, time_out = oracle.step(fx.params, state, case["actions"], rab_u=case["rab_u"],
+                                            turn_dur=case["turn_dur"], spawn_u=case["spawn_u"], yaw_u=case["yaw_u"])
+        critic = oracle.critic_state(fx.params, state)
+        try:
+            fixtures.compare(case, fx.params, state, obs, reward, time_out, critic, label=f"{mission}/{mode} t={t}")
+        except AssertionError as exc:
+            stats["violations"].append(str(exc)[:600])
+        post = case["post"]
+        stats["robot_steps"] += E * N
+        stats["resets"] += int(case["time_out"].sum())
+        stats["max_pos_err"] = max(stats["max_pos_err"], float(np.abs(state["pos"] - post["pos"]).max()))
+        stats["max_yaw_err"] = max(stats["max_yaw_err"], float(fixtures.angle_diff(state["yaw"], post["yaw"]).max()))
+        stats["max_obs_err"] = max(stats["max_obs_err"], float(np.abs(obs - case["obs"]).max()))
+        for name, marg in boundary_margins(fx.params, post["pos"], post["beh_cache"]).items():
+            # "on": the float32 value sits exactly on the boundary (e.g. a lone hit on the 90-degree IR sensor gives
+            # prox_angle == -float32(pi/2) in the reference too: pinned by test_prox_angle_boundary_matches_reference)
+            on = int((marg <= 4.4e-8).sum()) if name.startswith("|prox_angle|") else int((marg == 0.0).sum())
+            cur = stats["near_boundary"].setdefault(name, {"within_eps": 0, "of_which_exactly_on": 0})
+            cur["within_eps"] += int((marg < EPS).sum())
+            cur["of_which_exactly_on"] += on
+    return stats
+
+
+_RESULTS = []
+
+
+@pytest.mark.parametrize("mission", MISSIONS)
+@pytest.mark.parametrize("mode", MODES)
+def test_oracle_equals_live_reference_at_scale(mission, mode, capsys):
+    t0 = time.time()
+    st = run_case(mission, mode, TARGET)
+    st["seconds"] = round(time.time() - t0, 1)
+    _RESULTS.append(st)
+    with capsys.disabled():
+        near = {k: (v["within_eps"], v["of_which_exactly_on"]) for k, v in st["near_boundary"].items() if v["within_eps"]}
+        print(f"\n[live-reference parity] {mission}/{mode}: {st['robot_steps']} robot-steps, {st['resets']} env resets, "
+              f"pos<={st['max_pos_err']:.2e} yaw<={st['max_yaw_err']:.2e} obs<={st['max_obs_err']:.2e}, "
+              f"states within {EPS:g} of a boundary (of which exactly on it): {near if near else 'none'}, "
+              f"violations: {len(st['violations'])}")
+    if REPORT:
+        with open(REPORT, "w") as f:
+            json.dump({"eps": EPS, "target_robot_steps_per_case": TARGET, "torch": torch.__version__,
+                       "cases": _RESULTS}, f, indent=1)
+    assert st["robot_steps"] >= TARGET
+    assert not st["violations"], "\n".join(st["violations"][:5])

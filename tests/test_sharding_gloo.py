@@ -63,3 +63,50 @@ def test_metric_all_reduce_gloo_world2():
         assert set(results[r]) == set(METRIC_NAMES)
         for k, v in want.items():
             assert results[r][k] == v, (r, k, results[r][k], v)
+
+
+def _clock_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fixtures
+    from oracle_env import OracleBackedEnv
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = fixtures.make_cfg("xor", "cyclamen", 4)
+    cfg.episode_length_s = 1.0                       # L = 10 steps
+    env = OracleBackedEnv(cfg, env_offset=4 * rank)
+    env.reset()
+    # rank 0: counters 0,0,3,3 -> roll-overs 9 and 6 steps from now; rank 1: 0,7,7,9 -> 9, 2 and 0 steps from now
+    env.episode_length_buf = torch.tensor([0, 0, 3, 3] if rank == 0 else [0, 7, 7, 9])
+    clock = env.attach_job_reset_clock()
+    s0 = env._step_counter
+    bits = clock.bits(s0, 12)
+    seen = []
+    for t in range(12):   # the flag each step would be handed, and whether one of MY envs really timed out
+        _, _, to = env.step_tensor(torch.zeros(4, 20, 1, dtype=torch.long))
+        seen.append(bool(to.any()))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bits, seen))
+
+
+def test_job_reset_clock_is_job_wide_gloo_world2():
+    """The ENV:1262 any-reset flag of a sharded job: both ranks derive the SAME schedule, the OR of both shards'
+    roll-over phases, from one all-reduce; it matches the time-outs that then really happen."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_clock_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (b, s) for r, b, s in (q.get(timeout=180) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want_steps = {0, 2, 6, 9, 10}                      # phases {9, 6} | {9, 2, 0}, period 10, within 12 steps
+    want_bits = sum(1 << t for t in want_steps | {t + 10 for t in want_steps if t + 10 < 12})
+    assert res[0][0] == res[1][0] == want_bits
+    union = [a or b for a, b in zip(res[0][1], res[1][1])]
+    assert [t for t, hit in enumerate(union) if hit] == sorted(t for t in range(12) if (want_bits >> t) & 1)
