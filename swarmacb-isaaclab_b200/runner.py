@@ -102,8 +102,12 @@ def import_reference_agents(reference_root: str):
     """Import the reference's ``tasks/direct/agents`` package from a checkout, unmodified.  Its parents'
     ``__init__`` files need Omniverse, so they are replaced by bare namespace packages (the agents package
     itself imports only torch, yaml, tqdm and tensorboard)."""
-    pkg = os.path.join(reference_root, "source", "SwarmACB_isaac", "SwarmACB_isaac")
-    if not os.path.isdir(os.path.join(pkg, "tasks", "direct", "agents")):
+    # a git checkout (source/SwarmACB_isaac/SwarmACB_isaac) or a `pip install --target` directory (SwarmACB_isaac)
+    for pkg in (os.path.join(reference_root, "source", "SwarmACB_isaac", "SwarmACB_isaac"),
+                os.path.join(reference_root, "SwarmACB_isaac")):
+        if os.path.isdir(os.path.join(pkg, "tasks", "direct", "agents")):
+            break
+    else:
         raise FileNotFoundError(f"no SwarmACB_isaac/tasks/direct/agents under {reference_root}")
     for name, path in (("SwarmACB_isaac", pkg), ("SwarmACB_isaac.tasks", os.path.join(pkg, "tasks")),
                        ("SwarmACB_isaac.tasks.direct", os.path.join(pkg, "tasks", "direct"))):
@@ -114,8 +118,42 @@ def import_reference_agents(reference_root: str):
     return importlib.import_module("SwarmACB_isaac.tasks.direct.agents")
 
 
+def capture_rollout_stats(trainer, stats: dict):
+    """Record what the (unmodified) trainer measures about its own rollouts: the learned Option-Critic's
+    ``rollout_sps`` / ``rollout_seconds`` / ``update_seconds`` (agents/learned_option_critic_trainer.py:1840-1855,
+    handed to ``_write_update_diagnostics``), and for every trainer the wall clock of each ``collect_rollout`` call
+    with the device drained on both sides."""
+    import torch
+    stats.setdefault("rollout_sps", [])
+    stats.setdefault("rollout_seconds", [])
+    stats.setdefault("update_seconds", [])
+    stats.setdefault("collect_rollout_calls", [])
+    inner = trainer.collect_rollout
+
+    def timed_collect(*a, **k):
+        torch.cuda.synchronize()
+        t0, g0 = time.perf_counter(), trainer.global_step
+        out = inner(*a, **k)
+        torch.cuda.synchronize()
+        stats["collect_rollout_calls"].append({"seconds": time.perf_counter() - t0,
+                                               "agent_decisions": int(trainer.global_step - g0)})
+        return out
+
+    trainer.collect_rollout = timed_collect
+    if hasattr(trainer, "_write_update_diagnostics"):
+        diag = trainer._write_update_diagnostics
+
+        def tapped(metrics):
+            for k in ("rollout_sps", "rollout_seconds", "update_seconds"):
+                if k in metrics:
+                    stats[k].append(float(metrics[k]))
+            return diag(metrics)
+
+        trainer._write_update_diagnostics = tapped
+
+
 def run_reference_trainer(env, agents, yaml_path: str, *, total_timesteps: int | None = None, seed: int | None = None,
-                          log_dir: str | None = None, checkpoint_dir: str | None = None, tweak=None):
+                          log_dir: str | None = None, checkpoint_dir: str | None = None, tweak=None, hook=None):
     """scripts/train.py:191-203 with the reference's own loader and trainer classes."""
     _, _, cfg, _ = agents.load_config(yaml_path)
     if total_timesteps is not None:
@@ -132,6 +170,8 @@ def run_reference_trainer(env, agents, yaml_path: str, *, total_timesteps: int |
     cls = {"learned_option_critic": "LearnedOptionCriticTrainer", "option_critic": "FixedOptionCriticTrainer",
            "poca": "POCATrainer"}[trainer_type]
     trainer = getattr(agents, cls)(env, cfg)
+    if hook is not None:
+        hook(trainer)
     trainer.train()
     return trainer
 
@@ -180,6 +220,12 @@ def main(argv=None) -> int:
     ap.add_argument("--log-dir", default=None)
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--decisions", type=int, default=200, help="random-policy mode: decisions to run")
+    ap.add_argument("--horizon", type=int, default=None,
+                    help="trainer mode: override time_horizon (SURVEY 7.8: the OC2 buffer needs <= ~40 at 16384 envs)")
+    ap.add_argument("--updates", type=int, default=None,
+                    help="trainer mode: stop after this many rollout+update iterations (sets total_timesteps)")
+    ap.add_argument("--epochs", type=int, default=None, help="trainer mode: override num_epochs")
+    ap.add_argument("--report-json", default=None, help="trainer mode: write the captured rollout statistics here")
     args = ap.parse_args(argv)
 
     spec = load_run_spec(args.config)
@@ -193,9 +239,44 @@ def main(argv=None) -> int:
     from .env import make
     env = make(spec.task_id, cfg=cfg)
     if args.reference_root:
+        from .params import N
         agents = import_reference_agents(args.reference_root)
-        run_reference_trainer(env, agents, args.config, total_timesteps=args.total_timesteps, seed=args.seed,
-                              log_dir=args.log_dir, checkpoint_dir=args.checkpoint_dir)
+        stats: dict[str, Any] = {}
+
+        def tweak(tcfg):
+            if args.horizon is not None:
+                tcfg.horizon = int(args.horizon)
+                if hasattr(tcfg, "sequence_length"):
+                    tcfg.sequence_length = min(int(tcfg.sequence_length), int(args.horizon))
+            if args.epochs is not None:
+                tcfg.num_epochs = int(args.epochs)
+            if args.updates is not None:
+                # one iteration collects `horizon` decisions of every agent, then updates once
+                tcfg.buffer_size_hint = 0
+                tcfg.total_timesteps = int(args.updates) * int(tcfg.horizon) * env.num_envs * N
+            tcfg.summary_freq = max(int(getattr(tcfg, "summary_freq", 1)), 1)
+
+        t0 = time.perf_counter()
+        trainer = run_reference_trainer(env, agents, args.config, total_timesteps=args.total_timesteps, seed=args.seed,
+                                        log_dir=args.log_dir, checkpoint_dir=args.checkpoint_dir, tweak=tweak,
+                                        hook=lambda tr: capture_rollout_stats(tr, stats))
+        period = int(getattr(trainer, "decision_period", spec.decision_period))
+        calls = stats.get("collect_rollout_calls", [])
+        secs = sum(c["seconds"] for c in calls)
+        decs = sum(c["agent_decisions"] for c in calls)
+        report = {"run": spec.run_name, "task": spec.task_id, "variant": spec.variant, "trainer_type": spec.trainer_type,
+                  "trainer_class": type(trainer).__name__, "envs": env.num_envs, "decision_period": period,
+                  "horizon": int(trainer.cfg.horizon), "global_step": int(trainer.global_step),
+                  "wall_seconds": time.perf_counter() - t0,
+                  "trainer_rollout_sps": stats.get("rollout_sps"), "trainer_rollout_seconds": stats.get("rollout_seconds"),
+                  "trainer_update_seconds": stats.get("update_seconds"),
+                  "collect_rollout": {"calls": len(calls), "seconds": secs, "agent_decisions": decs,
+                                      "agent_decisions_per_s": decs / secs if secs else None,
+                                      "agent_steps_per_s": decs * period / secs if secs else None}}
+        print(json.dumps(report))
+        if args.report_json:
+            with open(args.report_json, "w") as f:
+                json.dump(report, f, indent=1)
     else:
         out: dict[str, Any] = {"run": spec.run_name, "task": spec.task_id, "variant": spec.variant,
                                "trainer_type": spec.trainer_type, "obs_dim": env.obs_dim,

@@ -23,8 +23,23 @@ import types
 
 import torch
 
+import os
+
 REF_ROOT = "/root/reference"
-_PKG = REF_ROOT + "/source/SwarmACB_isaac/SwarmACB_isaac"
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def find_reference_package():
+    """Directory of the reference's ``SwarmACB_isaac`` python package: the read-only checkout in the build container,
+    or the offline pip install under baseline/_ref (tools/install_reference.sh; that one travels to the GPU box)."""
+    for cand in (os.environ.get("SWARM_REFERENCE_PKG"), REF_ROOT + "/source/SwarmACB_isaac/SwarmACB_isaac",
+                 os.path.join(_REPO, "baseline", "_ref", "SwarmACB_isaac")):
+        if cand and os.path.isdir(os.path.join(cand, "tasks", "direct", "epuck")):
+            return cand
+    return None
+
+
+_PKG = find_reference_package() or REF_ROOT + "/source/SwarmACB_isaac/SwarmACB_isaac"
 
 MISSION_MODULES = {
     "dgt": ("directional_gate", "DirectionalGateEnv", "DirectionalGateEnvCfg"),

@@ -6,7 +6,8 @@ reference env classes run free (random actions, staggered episode counters so th
 all-env re-solve of ENV:1262 happen all along) from a warmed-up mid-episode state; every step is recorded with its
 noise (tests/golden/gen_golden.record_step) and replayed through the oracle teacher-forced.  Asserted: zero mismatches
 of counters / rewards / time-outs / FSM state / ground colours / mission flags, poses within 1e-5 m / 1e-5 rad,
-observations within 1e-4.  Reported ("report, not hide"): how many robot states came within 1e-6 of a zone
+observations within 1e-4 - except IR rays that graze an obstacle within 1e-6 m of a hit/miss boundary (a discontinuity
+of the sensor model, counted and reported as "grazing IR ray").  Reported ("report, not hide"): how many robot states came within 1e-6 of a zone
 or trigger threshold, i.e. how often a last-ulp difference between the oracle's deterministic sin/cos/atan2 and the
 reference's SLEEF values could have flipped a discrete outcome.
 
@@ -79,6 +80,69 @@ def boundary_margins(p, pos, beh_cache):
     return m
 
 
+def ray_decision_margin(p, pos, yaw, i, k):
+    """Smallest distance (m) of IR ray k of robot i to a hit/miss decision boundary of SENS:184-293, in float64:
+    tangency to a neighbour's disc, the ends of a wall segment, or the end of the sensor range.  A ray closer than
+    ~1e-6 m to one of them is a DISCONTINUITY of the sensor model: a last-ulp difference in the ray direction (SLEEF vs
+    the oracle's sin/cos) turns a grazing hit (reading up to 1 - t/range) into a miss (0).  The reference's own CPU and
+    CUDA builds disagree there in the same way."""
+    x, y, th = float(pos[i, 0]), float(pos[i, 1]), float(yaw[i])
+    ca, sa = float(p.cos_a[k]), float(p.sin_a[k])
+    dx, dy = ca * np.cos(th) - sa * np.sin(th), ca * np.sin(th) + sa * np.cos(th)
+    rng, r = float(p.prox_range), float(p.robot_radius)
+    best = np.inf
+    for j in range(N):
+        if j == i:
+            continue
+        ex, ey = float(pos[j, 0]) - x, float(pos[j, 1]) - y
+        proj = ex * dx + ey * dy
+        closest = np.sqrt(max(ex * ex + ey * ey - proj * proj, 0.0))
+        if proj > -1e-3 and closest < r + 1e-3:
+            hc = np.sqrt(max(r * r - min(closest, r) ** 2, 0.0))
+            best = min(best, abs(closest - r), abs(max(proj - hc, 0.0) - rng) if closest <= r else np.inf)
+    for g in range(int(p.n_segments)):
+        ax, ay, sx, sy = float(p.seg_ax[g]), float(p.seg_ay[g]), float(p.seg_sx[g]), float(p.seg_sy[g])
+        den = dx * sy - dy * sx
+        if abs(den) < 1e-9:
+            continue
+        ex, ey = ax - x, ay - y
+        t, u = (ex * sy - ey * sx) / den, (ex * dy - ey * dx) / den
+        slen = np.hypot(sx, sy)
+        if -1e-3 <= t <= rng + 1e-3 and -1e-3 <= u <= 1 + 1e-3:
+            best = min(best, abs(u) * slen, abs(1 - u) * slen, abs(t - rng), abs(t))
+    return best
+
+
+def explain_ray_flips(fx, case, obs, state):
+    """If every observation mismatch is an IR ray within EPS of a hit/miss boundary, patch those readings (and the
+    prox aggregate derived from them) to the reference's and return how many rays flipped; else return None."""
+    if fx.params.obs_dim != 24 and not fx.params.discrete_actions:
+        return None
+    post = case["post"]
+    flips = []
+    if fx.params.obs_dim == 24:
+        bad = np.argwhere(np.abs(obs - case["obs"]) > fixtures.SENSOR_TOL)
+        for e, i, c in bad:
+            if c >= 8 or ray_decision_margin(fx.params, post["pos"][e], post["yaw"][e], i, c) > EPS:
+                return None
+            flips.append((e, i, c))
+    else:   # 4-dim observations: the rays only show in the cached prox aggregate of the behaviour modules
+        bc, want = state["beh_cache"], post["beh_cache"]
+        bad = np.argwhere(np.abs(bc[:, 0] - want[:, 0]) > fixtures.SENSOR_TOL)
+        for e, i in bad:
+            if min(ray_decision_margin(fx.params, post["pos"][e], post["yaw"][e], i, k) for k in range(8)) > EPS:
+                return None
+            flips.append((e, i, -1))
+    if not flips:
+        return None
+    for e, i, c in flips:
+        if c >= 0:
+            obs[e, i, c] = case["obs"][e, i, c]
+        if fx.params.discrete_actions:
+            state["beh_cache"][e, 0:2, i] = post["beh_cache"][e, 0:2, i]
+    return len(flips)
+
+
 def run_case(mission, mode, target):
     sys.path.insert(0, os.path.join(HERE, "golden"))
     import gen_golden
@@ -115,16 +179,25 @@ def run_case(mission, mode, target):
         obs, reward, time_out = oracle.step(fx.params, state, case["actions"], rab_u=case["rab_u"],
                                             turn_dur=case["turn_dur"], spawn_u=case["spawn_u"], yaw_u=case["yaw_u"])
         critic = oracle.critic_state(fx.params, state)
+        post = case["post"]
+        stats["max_obs_err"] = max(stats["max_obs_err"], float(np.abs(obs - case["obs"]).max()))
         try:
             fixtures.compare(case, fx.params, state, obs, reward, time_out, critic, label=f"{mission}/{mode} t={t}")
         except AssertionError as exc:
-            stats["violations"].append(str(exc)[:600])
-        post = case["post"]
+            flipped = explain_ray_flips(fx, case, obs, state)
+            try:
+                if flipped is None:
+                    raise exc
+                fixtures.compare(case, fx.params, state, obs, reward, time_out, critic, label=f"{mission}/{mode} t={t}")
+                cur = stats["near_boundary"].setdefault("grazing IR ray (hit/miss flipped)",
+                                                        {"within_eps": 0, "of_which_exactly_on": 0})
+                cur["within_eps"] += flipped
+            except AssertionError as exc2:
+                stats["violations"].append(str(exc2)[:600])
         stats["robot_steps"] += E * N
         stats["resets"] += int(case["time_out"].sum())
         stats["max_pos_err"] = max(stats["max_pos_err"], float(np.abs(state["pos"] - post["pos"]).max()))
         stats["max_yaw_err"] = max(stats["max_yaw_err"], float(fixtures.angle_diff(state["yaw"], post["yaw"]).max()))
-        stats["max_obs_err"] = max(stats["max_obs_err"], float(np.abs(obs - case["obs"]).max()))
         for name, marg in boundary_margins(fx.params, post["pos"], post["beh_cache"]).items():
             # "on": the float32 value sits exactly on the boundary (e.g. a lone hit on the 90-degree IR sensor gives
             # prox_angle == -float32(pi/2) in the reference too: pinned by test_prox_angle_boundary_matches_reference)
