@@ -124,3 +124,24 @@ def test_rebinding_state_attributes_keeps_the_kernel_pointers():
     _, _, to = env.step_tensor(torch.zeros(64, N, 1, dtype=torch.long, device=DEV))
     assert bool(to.all())                       # the kernel saw the rebound counters: every env timed out
     assert int(env.episode_length_buf.max()) == 0
+
+
+def test_gym_make_builds_and_steps_the_env():
+    """scripts/train.py:188 on the GPU: gym.make(id, cfg=cfg) through the registration (gymnasium's API played by
+    tests/gym_stub.py, the package is not in this image) returns a working SwarmEnv."""
+    import gym_stub
+    from swarmacb_isaaclab_b200 import env as env_mod
+    from swarmacb_isaaclab_b200.cfg import TASK_CFGS
+    gym = gym_stub.install()
+    try:
+        assert env_mod.register_gym()
+        cfg = TASK_CFGS["SwarmACB-Sheltering-v0"]()
+        cfg.update_variant("daisy")
+        cfg.scene.num_envs, cfg.sim.device = 32, DEV
+        env = gym.make("SwarmACB-SHL-v0", cfg=cfg)          # the alias id of missions/sheltering/__init__.py:8-16
+        obs, _ = env.reset()
+        act = {a: torch.randint(0, 6, (32, 1), device=DEV) for a in env.possible_agents}
+        obs, rew, term, trunc, _ = env.unwrapped.step(act)
+        assert obs["epuck_7"].shape == (32, 24) and rew["epuck_0"].shape == (32,)
+    finally:
+        gym_stub.uninstall()

@@ -234,7 +234,13 @@ def test_bench_reference_arm_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "agent-steps/sec" and d["unit"] == "agent-steps/s"
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" = the unmodified torch env classes (when the reference package is importable: /root/reference here,
+    # baseline/_ref on the GPU box), else the C oracle port; the other arm is reported beside it
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert cb["port"]["kind"] == "port" and cb["port"]["value"] > 0 and "16384 envs" in cb["port"]["sample"]
+    if cb["kind"] == "reference":
+        assert cb["reference_torch"]["env_class"] == "ForagingEnv" and cb["reference_torch"]["envs"] == 1024
     assert d["e2e"] == {"value": d["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0
 
@@ -279,3 +285,36 @@ def test_state_attribute_assignment_copies_into_the_kernel_tensor():
     assert env.episode_length_buf.data_ptr() == ptr and env.episode_length_buf.tolist() == [5, 6, 7]
     env.agent_pos = torch.zeros(3, P.N, 2)
     assert float(env.agent_pos.abs().max()) == 0.0
+
+
+def test_gymnasium_registration_round_trip():
+    """missions/*/__init__.py + scripts/train.py:96-106,188 of the reference: the seven ids are registered with the
+    ``env_cfg_entry_point`` kwarg, the cfg class is resolved from ``gym.spec(id).kwargs`` and the env is built with
+    ``gym.make(id, cfg=cfg)``.  gymnasium is not installed here, so its registration API is played by tests/gym_stub.py;
+    on this CPU-only box the resolved entry point must be SwarmEnv refusing to run without CUDA."""
+    import importlib
+    import gym_stub
+    from swarmacb_isaaclab_b200 import env as env_mod
+    gym = gym_stub.install()
+    try:
+        assert env_mod.register_gym() is True
+        assert set(gym.registry) >= set(TASK_CFGS)
+        for tid, cfg_cls in TASK_CFGS.items():
+            spec = gym.spec(tid)
+            mod, _, name = spec.kwargs["env_cfg_entry_point"].partition(":")
+            assert getattr(importlib.import_module(mod), name) is cfg_cls          # scripts/train.py:96-106
+            assert spec.extra.get("disable_env_checker") is True
+        cfg = TASK_CFGS["SwarmACB-XOR-v0"]()
+        cfg.update_variant("cyclamen")
+        cfg.scene.num_envs = 2
+        if not torch.cuda.is_available():
+            cfg.sim.device = "cpu"
+            with pytest.raises(RuntimeError, match="CUDA"):
+                gym.make("SwarmACB-XOR-v0", cfg=cfg)                                 # scripts/train.py:188
+        # with gymnasium importable the per-agent spaces are gymnasium objects
+        from oracle_env import OracleBackedEnv
+        e = OracleBackedEnv(cfg)
+        assert isinstance(e.observation_space("epuck_0"), gym.spaces.Box) and e.observation_space("epuck_0").shape == (4,)
+        assert isinstance(e.action_space("epuck_3"), gym.spaces.Discrete) and e.action_space("epuck_3").n == 6
+    finally:
+        gym_stub.uninstall()
