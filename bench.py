@@ -143,12 +143,15 @@ def gen_actions(torch, discrete, T, E, device, seed=1):
     return torch.rand(T, E, N, 2, generator=g, device=device) * 2 - 1
 
 
-def time_steps(torch, env, actions, K, W, flush):
+def time_steps(torch, env, actions, K, W, flush, reward_acc=None):
     """W untimed + K timed env.steps; each timed step has its own CUDA-event pair on the launch stream so
-    the L2 flush between steps stays outside the timed region.  Returns per-step ms list."""
+    the L2 flush between steps stays outside the timed region.  Returns per-step ms list.  ``reward_acc``: a device
+    scalar that collects the team reward of every step (outside the timed regions)."""
     T = actions.shape[0]
     for w in range(W):
-        env.step_tensor(actions[w % T])
+        _, rew, _ = env.step_tensor(actions[w % T])
+        if reward_acc is not None:
+            reward_acc.add_(rew.sum())
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     torch.cuda.synchronize()
@@ -156,8 +159,10 @@ def time_steps(torch, env, actions, K, W, flush):
         if flush is not None:
             flush.add_(1.0)          # 512 MB read+write > 126 MB L2
         starts[k].record()
-        env.step_tensor(actions[(W + k) % T])
+        _, rew, _ = env.step_tensor(actions[(W + k) % T])
         stops[k].record()
+        if reward_acc is not None:
+            reward_acc.add_(rew.sum())
     torch.cuda.synchronize()
     return [s.elapsed_time(e) for s, e in zip(starts, stops)]
 
@@ -374,10 +379,11 @@ def measure_workload(torch, name, device, K, W, flush, env_offset_rank, want_e2e
     actions = gen_actions(torch, discrete, T, E, device)
     lib = _lib.load()
     l0 = lib.swarm_kernel_launch_count()
-    ms = time_steps(torch, env, actions, K, W, flush)
+    reward_acc = torch.zeros((), dtype=torch.float64, device=device)
+    ms = time_steps(torch, env, actions, K, W, flush, reward_acc)
     launches = lib.swarm_kernel_launch_count() - l0 - W
     res = {"env": env, "E": E, "mission": mission, "mode": mode, "task": task, "idx": idx, "ms": ms,
-           "launches": launches, "discrete": discrete}
+           "launches": launches, "discrete": discrete, "reward_acc": reward_acc}
     if want_e2e:
         # end-to-end through the C ABI with HOST buffers: pinned actions H2D, step, obs/reward/time_out D2H
         h_act = actions.cpu().pin_memory()
@@ -467,7 +473,7 @@ def main():
     from swarmacb_isaaclab_b200.sharding import EpisodeMetrics
     env = head["env"]
     em = EpisodeMetrics(device)
-    em.vec[3] = env._episode_group_reward.sum().double() + env.completed_group_reward.sum().double()
+    em.vec[3] = head["reward_acc"]          # team reward summed over every env and every step of the device-timed leg
     em.vec[4] = float(E * N * (K + W))
     metrics = em.reduce()   # NCCL all-reduce(sum) when world > 1
 

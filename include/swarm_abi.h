@@ -210,6 +210,10 @@ int swarm_host_step(const SwarmParams* params, const SwarmState* state, const vo
                     uint8_t* time_out_host, void* dev_actions, const SwarmOut* dev_out, int E,
                     void* stream);
 
+/* Destroys the library-owned copy streams / events of swarm_host_step (one set per device, created on first use).
+ * Optional: call it before cudaDeviceReset or when unloading the library. */
+int swarm_host_release(void);
+
 /* One tick of scripts/manual_control.py's loop (MC:721-757) for E standalone environments:
  *   SWARM_MC_PRE     sensors at the current pose (first RAB draw) + BehaviorModules.dispatch without
  *                    previous wheels (MC:729-749); robot 0 keeps the wheel command given in `wheels`

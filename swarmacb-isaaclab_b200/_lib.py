@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = (
     "swarm_step", "swarm_reset", "swarm_critic_state", "swarm_rollout", "swarm_host_step",
     "swarm_abi_version", "swarm_kernel_launch_count", "swarm_last_error_string", "swarm_fp32_peak",
-    "swarm_detmath_eval", "swarm_sync_episode_flags", "swarm_mc_tick", "swarm_mc_reset",
+    "swarm_detmath_eval", "swarm_sync_episode_flags", "swarm_mc_tick", "swarm_mc_reset", "swarm_host_release",
 )
 
 
@@ -37,6 +37,12 @@ def load(build_if_missing: bool = True):
         except Exception as exc:  # stale-but-present library is still usable on a box without nvcc
             if not os.path.exists(path):
                 raise SwarmLibraryError(f"libswarmstep.so is missing and could not be built: {exc}") from exc
+            if os.environ.get("SWARM_STRICT_BUILD"):
+                raise SwarmLibraryError(f"libswarmstep.so is older than its sources and the rebuild failed: {exc}") from exc
+            import warnings
+            warnings.warn(f"libswarmstep.so is OLDER than csrc/swarm_step.cu / swarm_abi.h and could not be rebuilt "
+                          f"({str(exc)[:200]}); loading the stale library (set SWARM_STRICT_BUILD=1 to make this an "
+                          f"error)", RuntimeWarning, stacklevel=2)
     if not os.path.exists(path):
         raise SwarmLibraryError(f"{path} not found; run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)
