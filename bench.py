@@ -503,6 +503,7 @@ def main():
     achieved_tf = alg_flops / (ms_step * 1e-3) / 1e12
     warm = time_steps(torch, env, gen_actions(torch, head["discrete"], 8, E, device, seed=2), K, 3, None)
     reset_ms = time_reset_steps(torch, env, gen_actions(torch, head["discrete"], 4, E, device, seed=4), 5, flush)
+    head_m5 = time_rollouts(torch, env, 5, min(K, 60), flush)   # the trainers' cadence: one action held for 5 steps
 
     others = {}
     if not args.no_others:
@@ -516,13 +517,12 @@ def main():
                                       "XOR env of configs[0] at the headline batch size",
                             "roofline": issue_roofline(prof.get(name), m, sms, sm_mhz, sm_src)}
             # the trainers' cadence (one action held for decision_period=5 motion updates, agents/poca_trainer.py:564-573)
-            # through SwarmEnv.rollout: one fused launch for wheel actions, 5 back-to-back launches for module actions
+            # through SwarmEnv.rollout: one fused launch per decision (module actions still run the sensors every step)
             m5 = time_rollouts(torch, r["env"], 5, min(K, 60), flush)
             others[name]["decision_period_5"] = {"value": r["E"] * N * 5 / (m5 * 1e-3), "unit": "agent-steps/s (1 GPU)",
                                                  "ms_per_decision": m5,
-                                                 "path": "swarm_rollout, fused kernel" if not r["discrete"] else
-                                                         "swarm_rollout, 5 launches"}
-            if not r["discrete"] and prof.get(name + "@rollout5"):
+                                                 "path": "swarm_rollout, fused kernel"}
+            if prof.get(name + "@rollout5"):
                 others[name]["decision_period_5"]["roofline"] = issue_roofline(prof[name + "@rollout5"], m5, sms, sm_mhz, sm_src)
             if name == "sheltering_oc2_16384":
                 # BASELINE.json configs[4] without its trainer (the reference's PyTorch code, not shipped here): the
@@ -586,6 +586,11 @@ def main():
                     "the kernel's exact culling skips most of them, so this is not a utilisation figure"},
         "per_rank": {"ms_per_step": per_rank_ms, "e2e_ms_per_step": per_rank_e2e_ms},
         "reset_step_ms": reset_ms,
+        "decision_period_5": {"value": E * N * 5 * world / (head_m5 * 1e-3) if world == 1 else None,
+                              "unit": "agent-steps/s (this rank's GPU)", "ms_per_decision": head_m5,
+                              "path": "SwarmEnv.rollout -> swarm_rollout, one fused launch per 5-step decision "
+                                      "(agents/poca_trainer.py:564-573)",
+                              "roofline": issue_roofline(prof.get(args.workload + "@rollout5"), head_m5, sms, sm_mhz, sm_src)},
         "ms_per_step_median": med_ms, "ms_per_step_warm_l2": sum(warm) / len(warm),
         "clocks": clocks,
         "episode_metrics": {"sum_group_reward": metrics["sum_group_reward"], "agent_steps": metrics["agent_steps"],

@@ -191,9 +191,9 @@ int swarm_critic_state(const SwarmParams* params, const SwarmState* state, float
 /* `steps` consecutive env.step calls with device-resident actions (steps,E,N[,2]); only the
  * last observation is kept, rewards are accumulated into out->reward, time_out is OR-ed.
  * actions_stride_steps = elements between consecutive steps (0 repeats one action: the trainers'
- * decision-period loop).  Wheel-action variants run as ONE fused launch per <= 32 steps (state in
- * registers between steps, sensors only after the last one); module-action variants as `steps`
- * back-to-back launches.  Either way the results equal `steps` swarm_step calls bit for bit.
+ * decision-period loop).  Runs as ONE fused launch per <= 32 steps (state in registers between
+ * steps; with wheel actions the sensors run only after the last one, module actions need them every
+ * step).  The results equal `steps` swarm_step calls bit for bit.
  * Injected noise tensors are rejected (single-step only). */
 int swarm_rollout(const SwarmParams* params, const SwarmState* state, const void* actions,
                   int64_t actions_stride_steps, const SwarmNoise* noise, const SwarmOut* out,

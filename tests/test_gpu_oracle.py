@@ -93,6 +93,44 @@ def test_cuda_vs_oracle_rollout(mission, mode, dec):
         assert np.abs(dev["completed_terminal_critic_state"] - host["completed_terminal_critic_state"]).max() <= 2e-5
 
 
+@pytest.mark.parametrize("mission,mode", [("shl", "daisy"), ("for", "oc2"), ("dgt", "cyclamen")])
+def test_crowded_queues_overflow_into_further_rounds(mission, mode):
+    """The sensor suite's per-warp work queues hold 64 / 64 / 32 items; whatever does not fit goes through another
+    round.  Here every packet survives (loss probability 0) and all 20 robots of every env sit in one 12-cm cluster:
+    ~600 range-and-bearing items and several hundred ray-disc items per warp, i.e. about ten rounds of every queue.
+    Results must still equal the oracle bit for bit."""
+    E = 96
+    rng = np.random.default_rng(21)
+    cfg = fixtures.make_cfg(mission, mode, E, device="cuda:0")
+    cfg.rab_loss_probability = 0.0
+    from swarmacb_isaaclab_b200.env import SwarmEnv
+    env = SwarmEnv(cfg)
+    p = env.params
+    host = oracle.new_state(E)
+    spawn_u, yaw_u = _cluster(rng, E, frac=1.0), rng.random((E, N), dtype=np.float32)
+    rab_u = rng.random((E, N, N), dtype=np.float32)
+    env.inject_noise(rab_u=rab_u, spawn_u=spawn_u, yaw_u=yaw_u)
+    env.reset()
+    obs_o = oracle.reset(p, host, rab_u=rab_u, spawn_u=spawn_u, yaw_u=yaw_u)
+    torch.cuda.synchronize()
+    assert np.array_equal(env._obs.cpu().numpy(), obs_o)
+    ztilde = obs_o[..., 19 if p.obs_dim == 24 else 3]
+    assert ztilde.mean() > 0.99          # every robot hears (almost) all 19 others
+    for t in range(3):
+        env.load_state(host)
+        act = rng.integers(0, 6, (E, N), dtype=np.int64) if p.discrete_actions else \
+            (rng.random((E, N, 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+        rab_u = rng.random((E, N, N), dtype=np.float32)
+        dur = rng.integers(1, 5, (E, N, 3)).astype(np.int32)
+        env.inject_noise(rab_u=rab_u, turn_dur=dur)
+        obs, rew, _ = env.step_tensor(torch.as_tensor(act, device="cuda:0"))
+        obs_o, rew_o, _ = oracle.step(p, host, act, rab_u=rab_u, turn_dur=dur)
+        dev = env.dump_state()
+        assert np.array_equal(dev["pos"], host["pos"]) and np.array_equal(dev["yaw"], host["yaw"]), t
+        assert np.array_equal(obs.cpu().numpy(), obs_o), t
+        assert np.array_equal(rew.cpu().numpy(), rew_o), t
+
+
 @pytest.mark.parametrize("mission,mode,E", [("hom", "lily", 4096), ("for", "daisy", 16384), ("dgt", "dandelion", 8192)])
 def test_full_size_properties(mission, mode, E):
     """BASELINE-size rollouts with in-kernel Philox noise: invariants that need no oracle."""
@@ -347,16 +385,16 @@ def test_host_buffer_step_equals_device_step(mission, mode, E):
     ("dgt", "dandelion", 1, 5, True), ("shl", "oc2", 1, 37, False), ("xor", "cyclamen", 2, 6, False),
     ("shl", "oc2c", 1, 5, True), ("dgt", "daisy", 1, 33, True),
 ])
-@pytest.mark.parametrize("fuse_discrete", [True, False])
-def test_fused_rollout_equals_single_steps(mission, mode, dec, T, repeat, fuse_discrete, monkeypatch):
+@pytest.mark.parametrize("fused", [True, False])
+def test_fused_rollout_equals_single_steps(mission, mode, dec, T, repeat, fused, monkeypatch):
     """swarm_rollout (T env.steps fused in one launch, state in registers, sensors skipped where nothing reads
     them) must leave exactly the state, last observation, summed reward and OR-ed time_out of T swarm_step
     calls on the same Philox stream - including envs that roll over inside the window, the all-env re-solve
     they trigger, and the single steps that follow the rollout (rotating any-reset flags rebuilt)."""
-    if fuse_discrete:   # exercise the fused kernel for the module-action variants too (default: back-to-back launches)
-        monkeypatch.setenv("SWARM_FUSE_DISCRETE", "1")
-    else:
-        monkeypatch.delenv("SWARM_FUSE_DISCRETE", raising=False)
+    if fused:           # the default: one fused launch per <= 32 steps, for wheel and module actions alike
+        monkeypatch.delenv("SWARM_UNFUSED_ROLLOUT", raising=False)
+    else:               # the fallback path: back-to-back single-step launches
+        monkeypatch.setenv("SWARM_UNFUSED_ROLLOUT", "1")
     E = 600
     a, b = _mk(mission, mode, E, dec), _mk(mission, mode, E, dec)
     a.reset(seed=11)

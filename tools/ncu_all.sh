@@ -7,7 +7,7 @@ for WL in foraging_daisy_16384 homing_lily_4096 dirgate_dandelion_8192 shelterin
   tools/ncu_capture.sh $WL gpurun_out/${PFX}_$WL 8 > /dev/null
   rm -f gpurun_out/${PFX}_$WL.ncu-rep     # the CSV exports carry everything quoted; gpurun_out/ is capped at 64 MiB
 done
-for WL in dirgate_dandelion_8192 sheltering_oc2_16384; do
+for WL in dirgate_dandelion_8192 sheltering_oc2_16384 foraging_daisy_16384 homing_lily_4096; do
   OUT=gpurun_out/${PFX}_${WL}_rollout5
   python tools/time_rollout.py 5 $WL > /dev/null 2>&1 || { echo "time_rollout failed"; exit 1; }
   ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:ELi2EEEv -s 12 -c 1 -f -o $OUT \
