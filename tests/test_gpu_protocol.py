@@ -145,3 +145,16 @@ def test_gym_make_builds_and_steps_the_env():
         assert obs["epuck_7"].shape == (32, 24) and rew["epuck_0"].shape == (32,)
     finally:
         gym_stub.uninstall()
+
+
+def test_viewer_feed_reads_one_env_from_device_state():
+    from swarmacb_isaaclab_b200 import viewer
+    env = _mk("for", "daisy", 128)
+    env.reset(seed=2)
+    act = torch.randint(0, 6, (128, N, 1), device=DEV)
+    for _ in range(3):
+        env.step_tensor(act)
+    sc, fr = viewer.scene(env), viewer.frame(env, 77)
+    assert np.array_equal(fr["pos"], env.agent_pos[77].cpu().numpy()) and fr["episode_step"] == 3
+    assert np.array_equal(fr["obs"], env._obs[77].cpu().numpy()) and fr["has_food"].shape == (N,)
+    assert viewer.render_svg(sc, fr).count('class="robot"') == N

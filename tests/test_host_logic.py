@@ -318,3 +318,24 @@ def test_gymnasium_registration_round_trip():
         assert isinstance(e.action_space("epuck_3"), gym.spaces.Discrete) and e.action_space("epuck_3").n == 6
     finally:
         gym_stub.uninstall()
+
+
+def test_viewer_feed_scene_frame_and_svg():
+    """the viewer feed - static scene from the SwarmParams block, one env's dynamic state, an SVG picture.
+    (host logic; device state is served by the oracle on CPU here, the GPU twin is in tests/test_gpu_protocol.py)"""
+    import fixtures
+    from oracle_env import OracleBackedEnv
+    from swarmacb_isaaclab_b200 import viewer
+    for mission, mode, n_walls, n_zones in (("shl", "daisy", 3, 3), ("dgt", "dandelion", 2, 2), ("for", "cyclamen", 0, 3)):
+        env = OracleBackedEnv(fixtures.make_cfg(mission, mode, 3))
+        env.reset()
+        sc = viewer.scene(env)
+        assert sc["arena_faces"].shape == (12, 4) and sc["internal_walls"].shape == (n_walls, 4) and len(sc["zones"]) == n_zones
+        fr = viewer.frame(env, 2)
+        assert fr["pos"].shape == (P.N, 2) and fr["obs"].shape == (P.N, env.obs_dim) and fr["episode_step"] == 0
+        assert np.array_equal(fr["pos"], env.agent_pos[2].numpy())
+        assert set(fr["behaviour"]) >= {"_explore_state", "_photo_avoiding", "_antiphoto_steps"}
+        svg = viewer.render_svg(sc, fr, selected=4)
+        assert svg.startswith("<svg") and svg.count('class="robot"') == P.N and svg.rstrip().endswith("</svg>")
+    with pytest.raises(IndexError):
+        viewer.frame(env, 3)
