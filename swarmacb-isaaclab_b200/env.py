@@ -82,6 +82,7 @@ class SwarmEnv:
         self._critic_pool = [torch.zeros(E, N, 5, **f32) for _ in range(self.CRITIC_POOL)] if fused_critic else []
         self._critic_slot = 0          # pool buffer the next fused write goes to
         self._critic_fresh = False     # that buffer holds get_critic_state() of the CURRENT state
+        self._critic_last = None       # tensor handed out for the CURRENT state (asked twice -> same tensor, no launch)
         self._critic_period = 0        # learned number of env.steps between two get_critic_state() calls
         self._steps_since_critic = 0
         self._terminated = torch.zeros(E, dtype=torch.bool, device=dev)
@@ -384,6 +385,7 @@ class SwarmEnv:
         """The SwarmOut block of the next call: with ``want`` the kernel also writes get_critic_state() of the state
         it leaves behind into the current pool buffer."""
         self._critic_fresh = bool(want)
+        self._critic_last = None           # the state is about to change: the tensor handed out last is history
         if not want:
             return self._out
         self._out_c.critic = self._critic_pool[self._critic_slot].data_ptr()
@@ -403,15 +405,20 @@ class SwarmEnv:
         if not self.fused_critic:
             out = torch.empty(self.num_envs, N, 5, dtype=torch.float32, device=self.device)
         else:
+            pose_now = (self._agent_pos._version, self._agent_yaw._version)
+            if self._critic_last is not None and self._pose_version == pose_now:
+                return self._critic_last   # asked again for the same state (OC2: next_critic_state, then critic_state)
             out = self._critic_pool[self._critic_slot]
             self._critic_slot = (self._critic_slot + 1) % self.CRITIC_POOL
             if self._steps_since_critic > 0:
                 self._critic_period = self._steps_since_critic
             self._steps_since_critic = 0
-            fresh = self._critic_fresh and self._pose_version == (self._agent_pos._version, self._agent_yaw._version)
+            fresh = self._critic_fresh and self._pose_version == pose_now
             self._critic_fresh = False
+            self._critic_last = out
             if fresh:
                 return out
+            self._pose_version = pose_now
         with self._device_guard():
             rc = self._lib.swarm_critic_state(C.byref(self.params), C.byref(self._state), C.c_void_p(out.data_ptr()),
                                               self.num_envs, self._stream())

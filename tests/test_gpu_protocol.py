@@ -98,6 +98,8 @@ def test_fused_critic_equals_standalone_kernel():
             b.step_tensor(act)
         ca, cb = a.get_critic_state(), b.get_critic_state()
         assert torch.equal(ca, cb), f"decision {d}"
+        n0 = _lib.load().swarm_kernel_launch_count()
+        assert a.get_critic_state() is ca and _lib.load().swarm_kernel_launch_count() == n0   # same state asked twice
         held.append((ca, cb.clone()))
         for ca_old, cb_old in held[-(a.CRITIC_POOL - 1):]:
             assert torch.equal(ca_old, cb_old)                               # still intact within the pool's horizon
