@@ -339,3 +339,17 @@ def test_viewer_feed_scene_frame_and_svg():
         assert svg.startswith("<svg") and svg.count('class="robot"') == P.N and svg.rstrip().endswith("</svg>")
     with pytest.raises(IndexError):
         viewer.frame(env, 3)
+
+
+def test_arena_face_tables_are_centrally_symmetric():
+    """The kernel's conservative face screening (cand_faces, the sensor suite's band tasks) gets all twelve signed
+    distances from six dot products: it relies on the regular dodecagon's central symmetry in the SwarmParams tables
+    (ENV:849-872: inward normal = -midpoint/|midpoint|, point = midpoint)."""
+    for m, cls in pkg.MISSION_CFGS.items():
+        p = P.build_params(cls())
+        inr = math.hypot(p.face_px[0], p.face_py[0])
+        for f in range(6):
+            assert abs(p.face_nx[f] + p.face_nx[f + 6]) < 1e-6 and abs(p.face_ny[f] + p.face_ny[f + 6]) < 1e-6, (m, f)
+        for f in range(12):
+            assert abs(p.face_px[f] * p.face_nx[f] + p.face_py[f] * p.face_ny[f] + inr) < 1e-6, (m, f)
+            assert abs(math.hypot(p.face_px[f], p.face_py[f]) - inr) < 1e-6
