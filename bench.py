@@ -167,6 +167,41 @@ def time_steps(torch, env, actions, K, W, flush, reward_acc=None):
     return [s.elapsed_time(e) for s, e in zip(starts, stops)]
 
 
+def time_back_to_back(torch, name, device, K, instances=4):
+    """The step without the ~5 us a CUDA-event pair adds around a lone launch (profiles/README.md, block times):
+    ``instances`` independent batches of the workload are stepped in turn, ONE event pair around all instances * K
+    launches.  Between two steps of the same batch the other batches touch more bytes than the L2 holds (the
+    contract's "inputs larger than L2" alternative to flushing), so every step still finds its state in HBM.
+    Secondary figure: the headline ``value`` stays the flushed, per-step-event number."""
+    from swarmacb_isaaclab_b200.env import SwarmEnv
+    mission, mode, E, _, _ = WORKLOADS[name]
+    envs = []
+    for i in range(instances):
+        env = SwarmEnv(make_cfg(mission, mode, E, device), env_offset=(1000 + i) * E)
+        env.reset(seed=i)
+        envs.append(env)
+    acts = gen_actions(torch, bool(envs[0].params.discrete_actions), 16, E, device, seed=5)
+    touched = E * N * (alg_bytes_per_agent_step(bool(envs[0].params.discrete_actions), envs[0].obs_dim, mission))
+    for w in range(3):
+        for env in envs:
+            env.step_tensor(acts[w])
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for k in range(K):
+        for env in envs:
+            env.step_tensor(acts[k % 16])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / (K * instances)
+    l2_mb = torch.cuda.get_device_properties(device).L2_cache_size / 1e6
+    return {"ms_per_step": ms, "value": E * N / (ms * 1e-3), "unit": "agent-steps/s (this rank's GPU)",
+            "instances": instances, "steps_per_instance": K,
+            "mb_touched_between_revisits": touched * (instances - 1) / 1e6, "l2_mb": l2_mb,
+            "note": "one event pair around instances * steps launches of independent batches stepped in turn; "
+                    "secondary - `value` is the flushed per-step-event figure"}
+
+
 def time_rollouts(torch, env, T, reps, flush):
     """Mean ms of one decision = SwarmEnv.rollout(action, T) with a fresh random action per decision (L2 flushed)."""
     E = env.num_envs
@@ -504,6 +539,7 @@ def main():
     warm = time_steps(torch, env, gen_actions(torch, head["discrete"], 8, E, device, seed=2), K, 3, None)
     reset_ms = time_reset_steps(torch, env, gen_actions(torch, head["discrete"], 4, E, device, seed=4), 5, flush)
     head_m5 = time_rollouts(torch, env, 5, min(K, 60), flush)   # the trainers' cadence: one action held for 5 steps
+    back_to_back = time_back_to_back(torch, args.workload, device, min(K, 100))
 
     others = {}
     if not args.no_others:
@@ -586,6 +622,7 @@ def main():
                     "the kernel's exact culling skips most of them, so this is not a utilisation figure"},
         "per_rank": {"ms_per_step": per_rank_ms, "e2e_ms_per_step": per_rank_e2e_ms},
         "reset_step_ms": reset_ms,
+        "back_to_back": back_to_back,
         "decision_period_5": {"value": E * N * 5 * world / (head_m5 * 1e-3) if world == 1 else None,
                               "unit": "agent-steps/s (this rank's GPU)", "ms_per_decision": head_m5,
                               "path": "SwarmEnv.rollout -> swarm_rollout, one fused launch per 5-step decision "
