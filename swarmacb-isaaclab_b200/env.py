@@ -343,6 +343,9 @@ class SwarmEnv:
                              f"(T, {E}, {N}, {A}) (one per step), got {shape}")
         if T <= 0:
             raise ValueError("rollout: steps must be > 0")
+        if self.job_reset_clock is not None and T > 32:
+            raise ValueError("rollout: with a job-wide reset clock attached one call covers at most 32 steps "
+                             "(SwarmNoise.any_reset_bits is a 32-bit schedule)")
         if actions.dtype != want or actions.device != self.device:
             actions = actions.to(device=self.device, dtype=want)
         actions = actions.contiguous()

@@ -273,6 +273,13 @@ def test_rollout_rejects_ambiguous_or_short_action_buffers():
     env.reset()
     env.rollout(torch.zeros(E, E, P.N, dtype=torch.long))
     assert int(env.episode_length_buf[0]) == E
+    # a job-wide reset clock hands the kernel a 32-bit schedule: longer calls are refused BEFORE any state advances
+    env.attach_job_reset_clock()
+    counter = env._step_counter
+    with pytest.raises(ValueError):
+        env.rollout(torch.zeros(E, P.N, 1, dtype=torch.long), 33)
+    assert env._step_counter == counter
+    env.rollout(torch.zeros(E, P.N, 1, dtype=torch.long), 32)
 
 
 def test_state_attribute_assignment_copies_into_the_kernel_tensor():
